@@ -1,0 +1,101 @@
+"""Pins oracle/ref_port.py: (a) against the committed golden vectors written by the
+real reference (tests/golden/make_golden.py), (b) against the live reference when
+/root/reference is present (build container only).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle.ref_port import RefPort
+from oracle import ref_harness
+from tests.util import load_golden, poses_from, obs_from, as3
+
+PIPE_CASES = ["pipe_c2_m1", "pipe_c4_m4", "pipe_c8_m16"]
+
+
+def _blobs(port, frames, b, c):
+    pts = port.find_dot(as3(frames[b, c]))
+    return [p for p in pts if p[0] is not None]
+
+
+@pytest.mark.parametrize("name", PIPE_CASES + ["blobs_irregular"])
+def test_find_dot_matches_golden(name):
+    z = load_golden(name)
+    frames = z["frames"]
+    B, C = frames.shape[:2]
+    port = RefPort([np.eye(3)] * C)
+    step = max(1, B // 12)
+    for b in range(0, B, step):
+        for c in range(C):
+            pts = _blobs(port, frames, b, c)
+            n = int(z["blob_n"][b, c])
+            assert len(pts) == n
+            assert np.array_equal(np.array(pts, dtype=np.int32).reshape(n, 2), z["blob_xy"][b, c, :n])
+
+
+@pytest.mark.parametrize("name", PIPE_CASES)
+def test_match_and_triangulate_matches_golden(name):
+    z = load_golden(name)
+    C = int(z["C"])
+    port = RefPort([z["K"]] * C)
+    poses = poses_from(z)
+    B = z["blob_n"].shape[0]
+    step = max(1, B // 8)
+    for b in range(0, B, step):
+        pts = [[list(map(int, z["blob_xy"][b, c, i])) for i in range(z["blob_n"][b, c])] for c in range(C)]
+        err, obj, _ = port.match_and_triangulate(pts, poses)
+        k = int(z["nroot"][b])
+        assert len(err) == k
+        # same third-party routines, same order of operations -> bit-identical
+        assert np.array_equal(np.asarray(obj, dtype=np.float64).reshape(k, 3), z["obj"][b, :k])
+        assert np.array_equal(err, z["err"][b, :k])
+
+
+@pytest.mark.parametrize("name", ["tri_c4", "tri_c8", "tri_c16"])
+def test_triangulate_and_error_match_golden(name):
+    z = load_golden(name)
+    C = z["R"].shape[0]
+    port = RefPort([z["K"]] * C)
+    obs = obs_from(z)
+    poses = poses_from(z)
+    X = port.triangulate_many(obs, poses)
+    assert np.array_equal(np.asarray(X, dtype=np.float64), z["X"])
+    assert np.array_equal(port.reprojection_errors(obs, X, poses), z["err"])
+
+
+def test_triangulate_needs_two_views():
+    port = RefPort([np.eye(3)] * 2)
+    poses = [{"R": np.eye(3), "t": np.zeros(3)}, {"R": np.eye(3), "t": np.array([-1.0, 0, 0])}]
+    assert port.triangulate_one([[10, 10], [None, None]], poses) == [None, None, None]
+    assert port.reprojection_error([[10, 10], [None, None]], np.zeros(3), poses) is None
+    assert port.find_dot(np.zeros((480, 640, 3), np.uint8)) == [[None, None]]
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree only exists in the build container")
+def test_port_equals_live_reference(synth):
+    C, M = 4, 6
+    helpers, cams = ref_harness.load_reference(C)
+    frames, truth, poses, K = synth.make_frame_pool(C, M, 3, seed=42)
+    port = RefPort([K] * C)
+    for b in range(3):
+        ref_pts = [cams._find_dot(as3(frames[b, c]))[1] for c in range(C)]
+        my_pts = [port.find_dot(as3(frames[b, c])) for c in range(C)]
+        assert ref_pts == my_pts
+        e, o, _ = helpers.find_point_correspondance_and_object_points([list(map(list, p)) for p in ref_pts], poses, [None] * C)
+        e2, o2, _ = port.match_and_triangulate(my_pts, poses)
+        assert np.array_equal(e, e2)
+        assert np.array_equal(np.asarray(o, dtype=np.float64), np.asarray(o2, dtype=np.float64))
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree only exists in the build container")
+def test_ba_residuals_equal_live_reference(synth):
+    C = 3
+    helpers, cams = ref_harness.load_reference(C)
+    obs, poses, K, _ = synth.make_tracks(C, 12, seed=2)
+    start = synth.perturb_poses(poses, seed=3)
+    port = RefPort([K] * C)
+    X = helpers.triangulate_points(obs, start)
+    r_ref = helpers.calculate_reprojection_errors(obs, X, start).astype(np.float32)
+    x0 = port.poses_to_params(start)
+    r = port.ba_residuals(x0, obs)
+    # poses -> rotvec -> matrix round trip in the port: equal to float32 resolution
+    assert r.dtype == np.float32 and r.shape == r_ref.shape
+    assert np.allclose(r, r_ref, rtol=1e-5, atol=1e-6)
