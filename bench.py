@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- mocap frame-sets/s of the B200 marker-tracking core (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path (S1 blob detection -> S2 epipolar matching -> S3 DLT
+triangulation + reprojection error, one launch group per batch) over one batch of synthetic
+frame-sets.  Workload at N = 1: BASELINE config 2 -- 4 cameras, 4 markers, 10 000 frame-sets of
+640x480 uint8 per step, resident in HBM (12.3 GB >> L2, so every step reads HBM).  N > 1:
+one process per GPU (torchrun), every rank owns its own 10 000-frame-set shard of the stream
+(round-robin ownership, weak scaling) and the ranks exchange ONE NCCL all-gather of 3D track
+records per batch.
+
+Printed JSON line (rank 0): value = whole-job frame-sets/s with inputs resident in HBM;
+e2e = the same through the host-buffer C-ABI call (pinned host frames, H2D + D2H inside the
+timed region); roofline = the dominant kernel (k_threshold_segments) against the measured HBM
+peak; cpu_baseline = the oracle port (the reference's own cv2/numpy/scipy call sequence) on
+this box's host cores on a bounded sample.
+
+--impl reference times the reference's CPU implementation (oracle port: the reference is
+Python and /root/reference does not exist on the GPU box) on all host cores, same workload
+shape, bounded sample per step.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CAM, N_MARKERS, BATCH = 4, 4, 10000
+POOL = 250                       # distinct rendered frame-sets; the batch cycles through them
+WIDTH, HEIGHT = 640, 480
+MAX_ROOTS = 16
+HBM_FALLBACK_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+# ------------------------------------------------------------------------------------------------
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_pool():
+    synth = importlib.import_module("low-cost-mocap_b200.synth")
+    return synth.make_frame_pool(N_CAM, N_MARKERS, POOL, seed=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the oracle port, one worker process per core (the reference itself is single-threaded
+# Python; frame-sets are independent, so fanning out over processes is the most it can use)
+_W = {}
+
+
+def _cpu_init(K, poses):
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle.ref_port import RefPort
+    _W["port"] = RefPort([K] * len(poses))
+    _W["poses"] = poses
+
+
+def _cpu_one(frame_set):
+    port, poses = _W["port"], _W["poses"]
+    pts = [port.find_dot(np.repeat(img[:, :, None], 3, axis=2)) for img in frame_set]
+    e, o, _ = port.match_and_triangulate(pts, poses)
+    return len(e)
+
+
+def cpu_pass(pool_obj, frames, n_sets):
+    t0 = time.perf_counter()
+    got = pool_obj.map(_cpu_one, [frames[i % len(frames)] for i in range(n_sets)], chunksize=max(1, n_sets // (8 * pool_obj._processes)))
+    return time.perf_counter() - t0, sum(got)
+
+
+def run_reference_arm(args):
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames, truth, poses, K = make_pool()
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(K, poses)) as pool_obj:
+        # size one step to ~4 s of wall time on this box
+        cpu_pass(pool_obj, frames, cores * 2)                      # spin the workers up
+        t_probe, _ = cpu_pass(pool_obj, frames, cores * 2)
+        per_set = t_probe / (cores * 2)
+        sample = int(min(BATCH, max(cores * 4, 4.0 / per_set)))
+        for _ in range(args.warmup):
+            cpu_pass(pool_obj, frames, max(cores, sample // 4))
+        t = 0.0
+        for _ in range(args.steps):
+            dt, _ = cpu_pass(pool_obj, frames, sample)
+            t += dt
+    value = sample * args.steps / t
+    line = {
+        "impl": "reference", "metric": "mocap frame-sets/s (4-cam 640x480 synthetic, blob+epipolar+DLT)",
+        "value": value, "unit": "frame-sets/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 pixels -> int64 moments -> f64 geometry", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2: 4 cameras, 4 markers, 640x480 uint8 frame-sets; "
+                               f"bounded sample of {sample} frame-sets per step of the 10000-frame-set batch",
+                   "cameras": N_CAM, "markers": N_MARKERS, "frame_sets_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "frame-sets/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} frame-sets per step x {args.steps} steps, one worker process per core"},
+        "e2e": {"value": value, "unit": "frame-sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("low-cost-mocap_b200")
+    sharding = importlib.import_module("low-cost-mocap_b200.sharding")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N > 1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    frames, truth, poses, K = make_pool()
+    ctx = pkg.MocapContext(N_CAM, WIDTH, HEIGHT, device=local, max_roots=MAX_ROOTS)
+    ctx.set_cameras([K] * N_CAM, poses)
+
+    # every rank owns BATCH frame-sets of the global stream of world*BATCH (round-robin ownership);
+    # content cycles through the rendered pool, offset per rank so shards differ
+    pool_dev = torch.from_numpy(frames).to(dev)
+    owned = torch.from_numpy(sharding.shard_indices(BATCH * world, rank, world)).to(dev)
+    batch = pool_dev[owned % POOL].contiguous()                   # [BATCH, C, H, W] uint8, 12.3 GB
+    del pool_dev
+    out = ctx.alloc_tracks(BATCH, dev)
+    bytes_per_step = batch.numel()
+
+    def step():
+        ctx.pipeline(batch, out=out)
+        if world > 1:
+            rec = sharding.pack_tracks(out["obj"], out["err"], out["n"])
+            return sharding.all_gather_tracks(rec, BATCH * world)
+        return None
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sync_all()
+
+    # ---- timed region: resident inputs -----------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.enable_kernel_timing(True)
+    ctx.detect_kernel_ms(reset=True)
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = ctx.launch_count() - launches0
+    if world > 1:
+        launches += 5 * args.steps          # pack (3 slice copies + cast) + transpose copy of the gather, torch kernels
+    kern_ms, kern_n = ctx.detect_kernel_ms(reset=True)
+    ctx.enable_kernel_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    value = BATCH * world * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI host entry point --------------------------------
+    host_frames = torch.empty(batch.shape, dtype=torch.uint8).pin_memory()
+    host_frames.copy_(batch)
+    host_out = {"obj": torch.empty((BATCH, MAX_ROOTS, 3), dtype=torch.float64).pin_memory(),
+                "err": torch.empty((BATCH, MAX_ROOTS), dtype=torch.float64).pin_memory(),
+                "n": torch.empty((BATCH,), dtype=torch.int32).pin_memory(),
+                "flags": torch.empty((BATCH,), dtype=torch.int32).pin_memory()}
+    e2e_steps = max(1, min(args.steps, 3))
+    ctx.pipeline_host(host_frames, out=host_out)                  # warm-up (allocates staging)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.pipeline_host(host_frames, out=host_out)              # returns with results in host memory
+    torch.cuda.synchronize(dev)
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = BATCH * world * e2e_steps / float(dt.item())
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+    same = bool((host_out["n"].to(dev) == out["n"]).all().item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg_bytes = bytes_per_step                               # C*W*H bytes per frame-set, read once
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+        # ---- CPU baseline: the oracle port on this box, bounded sample ---------------------
+        import multiprocessing as mp
+        cores = os.cpu_count() or 1
+        mctx = mp.get_context("fork")
+        with mctx.Pool(cores, initializer=_cpu_init, initargs=(K, poses)) as pool_obj:
+            cpu_pass(pool_obj, frames, cores * 2)                  # spin the workers up
+            t_probe, _ = cpu_pass(pool_obj, frames, cores * 2)
+            sample = int(min(BATCH, max(cores * 4, 10.0 / (t_probe / (cores * 2)))))
+            t_cpu, cpu_points = cpu_pass(pool_obj, frames, sample)
+        gpu_points = int(out["n"][:1].sum().item())
+        line = {
+            "metric": "mocap frame-sets/s (4-cam 640x480 synthetic, blob+epipolar+DLT)",
+            "value": value, "unit": "frame-sets/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 pixels -> int64 moments -> f64 geometry", "data": "synthetic",
+            "config": {"workload": "BASELINE config 2: 4 cameras, 4 markers, 10000 frame-sets of 640x480 uint8 per GPU per step, "
+                                   "S1 blob + S2 epipolar + S3 DLT",
+                       "cameras": N_CAM, "markers": N_MARKERS, "frame_sets_per_step_per_gpu": BATCH,
+                       "distinct_frame_sets": POOL, "l2": "inputs (12.3 GB per step) larger than L2, no flush needed",
+                       "parallelism": f"frame-set round-robin over {world} GPU(s), one NCCL all-gather of tracks per batch" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "frame-sets/s", "h2d_bytes_per_step": int(bytes_per_step),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "matches_resident_path": same},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_threshold_segments_c1", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes // max(1, kern_n // args.steps)) if kern_n else None,
+                         "avg_launch_ms": kern_ms, "launches_timed": kern_n,
+                         "whole_step_frac": (bytes_per_step * args.steps / (ms_total * 1e-3) / 1e9) / peak},
+            "cpu_baseline": {"value": sample / t_cpu, "unit": "frame-sets/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} frame-sets of the same workload, one worker process per core"},
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,201 @@
+/*
+ * mocap_b200.h -- C ABI of libmocap_b200.so: the B200 (sm_100a) multi-view
+ * marker-tracking core that stands in for the per-frame geometry path of
+ * jyjblrd/Low-Cost-Mocap, computer_code/api/helpers.py.
+ *
+ * The reference has no FFI of its own: its hot path is five module-level Python
+ * functions.  Each entry point below names the reference function (file:line,
+ * relative to the reference repository) it replaces; the Python mirror that
+ * re-creates the reference signatures on top of this ABI lives in
+ * low-cost-mocap_b200/api.py and the binding a maintainer adds is shown in
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no torch / numpy types.
+ *   - every function returns MOCAP_OK (0) or a negative MOCAP_E* code;
+ *     mocap_last_error(ctx) gives the text of the last failure of that ctx.
+ *   - "_dev" entry points take DEVICE pointers and only enqueue work on the
+ *     context's stream (mocap_set_stream); they never synchronise.
+ *     "_host" entry points take HOST pointers, copy in/out and return when the
+ *     results are in the host buffers.
+ *   - one context per host thread (the reference's Cameras singleton is
+ *     unsynchronised, Singleton.py:3); contexts are independent.
+ *   - there is no CPU fallback: without a CUDA device every call fails with
+ *     MOCAP_ENODEV.
+ *
+ * Layouts (row-major, innermost last)
+ *   frames      uint8  [n_frame_sets][n_cam][H][W]        (channels == 1)
+ *               uint8  [n_frame_sets][n_cam][H][W][3]     (channels == 3, the
+ *               layout Cameras._find_dot receives, helpers.py:143)
+ *   blob_xy     int32  [n_images][max_blobs][2]   (x, y) = int(m10/m00), int(m01/m00)
+ *   blob_n      int32  [n_images]                 n_images = n_frame_sets * n_cam
+ *   blob_mom    int64  [n_images][max_blobs][4]   {2*m00, 6*m10, 6*m01, pixel count}
+ *   img_flags   int32  [n_images]                 MOCAP_F_* bits
+ *   obj         double [n_frame_sets][max_roots][3]
+ *   err         double [n_frame_sets][max_roots]  mean squared reprojection error, px^2
+ *   n_obj       int32  [n_frame_sets]
+ *   set_flags   int32  [n_frame_sets]             MOCAP_F_* bits
+ *   chosen      int32  [n_frame_sets][max_roots][n_cam]  blob index per camera of the
+ *                                                 winning correspondence, -1 = no view
+ */
+#ifndef MOCAP_B200_H
+#define MOCAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOCAP_OK          0
+#define MOCAP_EINVAL     -1   /* bad argument                                  */
+#define MOCAP_ENODEV     -2   /* no usable CUDA device / wrong architecture    */
+#define MOCAP_ECUDA      -3   /* a CUDA runtime call failed                    */
+#define MOCAP_ENOMEM     -4
+#define MOCAP_ESTATE     -5   /* e.g. cameras not set                          */
+
+/* per-image / per-frame-set overflow flags (results for that unit are truncated) */
+#define MOCAP_F_SEGMENTS  1   /* more above-threshold 16-px segments than max_segments */
+#define MOCAP_F_BLOBS     2   /* more blobs than max_blobs                               */
+#define MOCAP_F_ROOTS     4   /* more roots than max_roots                               */
+#define MOCAP_F_CANDS     8   /* more than max_cands candidates on one epipolar line     */
+#define MOCAP_F_GROUPS   16   /* more than max_groups candidate groups for one root      */
+
+#if defined(__GNUC__)
+#define MOCAP_API __attribute__((visibility("default")))
+#else
+#define MOCAP_API
+#endif
+
+typedef struct mocap_ctx mocap_ctx;
+
+typedef struct mocap_config {
+    int device;         /* CUDA device ordinal                                            */
+    int n_cam;          /* cameras per frame-set (1..16)                                   */
+    int width;          /* image width, multiple of 16 (640)                              */
+    int height;         /* image height (480)                                             */
+    int max_blobs;      /* blobs kept per image (<= 64)                                   */
+    int max_segments;   /* above-threshold 16-px segments handled per image (power of two, 64..4096) */
+    int max_roots;      /* roots per frame-set in the matcher (<= 128)                    */
+    int max_cands;      /* candidates kept per (root, camera) (<= 16)                     */
+    int max_groups;     /* candidate groups evaluated per root                            */
+} mocap_config;
+
+/* Fills *cfg with defaults for n_cam cameras of width x height. */
+MOCAP_API void mocap_default_config(mocap_config* cfg, int n_cam, int width, int height);
+
+MOCAP_API int  mocap_create(mocap_ctx** out, const mocap_config* cfg);
+MOCAP_API void mocap_destroy(mocap_ctx* ctx);
+MOCAP_API const char* mocap_last_error(const mocap_ctx* ctx);
+/* Text for a status when no context exists (mocap_create failed). */
+MOCAP_API const char* mocap_status_string(int status);
+
+/* cudaStream_t on which all *_dev work is enqueued (NULL = the legacy default stream). */
+MOCAP_API int mocap_set_stream(mocap_ctx* ctx, void* cuda_stream);
+
+/* Camera model of the session.  HOST pointers: K[n_cam][9], R[n_cam][9], t[n_cam][3],
+ * row-major doubles.  Replaces the state the reference keeps in
+ * Cameras.camera_params (helpers.py:19-22,188-193) and in the camera_poses list
+ * every hot-path function receives (helpers.py:293,339; set at helpers.py:171-175).
+ * Builds on the host, once: P_kc = K_k [R_c|t_c] (helpers.py:305-308,351-355) and the
+ * fundamental matrices F_rc of every ordered camera pair
+ * (cv.sfm.fundamentalFromProjections, helpers.py:362). */
+MOCAP_API int mocap_set_cameras(mocap_ctx* ctx, const double* K, const double* R, const double* t);
+
+/* Optional epilogue of the matcher: object points leave in world coordinates
+ * (helpers.py:96-103: flip x,y; 4x4 to_world_coords_matrix; dehomogenise; swap y,z).
+ * M = NULL switches it off (default).  HOST pointer, 16 doubles row-major. */
+MOCAP_API int mocap_set_world_transform(mocap_ctx* ctx, const double* M);
+
+/* S1 -- replaces Cameras._find_dot (helpers.py:143-163) for n_images images at once:
+ * gray (cvtColor RGB2GRAY when channels == 3), pix > threshold, 8-connected blobs,
+ * contour-polygon moments, centre = int(m10/m00), int(m01/m00); zero-area blobs are
+ * dropped; blobs leave in cv.findContours order (descending raster position of the
+ * blob's first pixel).  blob_mom and img_flags may be NULL. */
+MOCAP_API int mocap_detect_dev(mocap_ctx* ctx, const uint8_t* frames, int n_images, int channels,
+                     int threshold, int32_t* blob_xy, int32_t* blob_n,
+                     int64_t* blob_mom, int32_t* img_flags);
+
+/* S2+S3 -- replaces find_point_correspondance_and_object_points (helpers.py:339-421),
+ * incl. the triangulate_points / calculate_reprojection_errors calls inside it
+ * (helpers.py:408-419), for n_frame_sets frame-sets at once.  Input is the output of
+ * mocap_detect_dev.  chosen and set_flags may be NULL. */
+MOCAP_API int mocap_match_triangulate_dev(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n,
+                                int n_frame_sets, double* obj, double* err, int32_t* n_obj,
+                                int32_t* set_flags, int32_t* chosen);
+
+/* S1+S2+S3 back to back on the context's stream, intermediate blob lists kept in
+ * context-owned device memory: the per-frame body of Cameras._camera_read
+ * (helpers.py:84-103) without capture/preprocessing. */
+MOCAP_API int mocap_pipeline_dev(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets, int channels,
+                       int threshold, double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
+
+/* Same with HOST buffers: frames are copied to the device in chunks overlapped with
+ * compute, results copied back; returns after the results are in the host buffers.
+ * For best speed pass page-locked memory (mocap_host_alloc). */
+MOCAP_API int mocap_pipeline_host(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets, int channels,
+                        int threshold, double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
+
+/* S3 -- replaces triangulate_points (helpers.py:330-336) and
+ * calculate_reprojection_errors (helpers.py:203-211) on explicit correspondences.
+ * obs double [n_points][n_cam][2], mask uint8 [n_points][n_cam] (0 = [None, None]).
+ * X double [n_points][3], err double [n_points], valid uint8 [n_points]
+ * (0 where the reference returns [None]*3 / None, i.e. fewer than two views).
+ * err may be NULL.  DEVICE pointers. */
+MOCAP_API int mocap_triangulate_dev(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points,
+                          double* X, double* err, uint8_t* valid);
+/* HOST-pointer convenience form of the above. */
+MOCAP_API int mocap_triangulate_host(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points,
+                           double* X, double* err, uint8_t* valid);
+/* calculate_reprojection_errors for GIVEN points (helpers.py:203-241). HOST pointers. */
+MOCAP_API int mocap_reprojection_errors_host(mocap_ctx* ctx, const double* obs, const uint8_t* mask,
+                                   const double* X, int n_points, double* err, uint8_t* valid);
+
+/* S4 -- replaces bundle_adjustment (helpers.py:244-290): robust (Cauchy) trust-region
+ * least squares over the poses of cameras 1..C-1 (rotation vector + translation;
+ * camera 0 pinned at (I,0); the reference's focal parameters are dead, helpers.py:267-270),
+ * residual_j = float32(mean squared reprojection error of point j after DLT
+ * re-triangulation with the trial poses).  HOST pointers; R,t are in/out. */
+typedef struct mocap_ba_options {
+    double ftol;        /* 1e-2  (helpers.py:288)                */
+    double xtol;        /* 1e-8  (scipy default)                 */
+    double gtol;        /* 1e-8  (scipy default)                 */
+    int    max_nfev;    /* 0 -> 100 * n_params (scipy default)   */
+    int    jacobian;    /* 0: 2-point finite differences (scipy default, what the reference runs) */
+} mocap_ba_options;
+
+typedef struct mocap_ba_report {
+    double cost_initial;   /* 0.5 * sum log1p(r^2) at the start                 */
+    double cost_final;
+    double optimality;     /* ||J^T f||_inf at the end                           */
+    int    n_iterations;
+    int    n_fev;          /* residual-vector evaluations (each = n_points DLTs) */
+    int    status;         /* scipy-style: 0 max_nfev, 1 gtol, 2 ftol, 3 xtol, 4 both */
+    int    n_residuals;
+} mocap_ba_report;
+
+MOCAP_API void mocap_ba_default_options(mocap_ba_options* opt);
+MOCAP_API int  mocap_bundle_adjust_host(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points,
+                              double* R, double* t, const mocap_ba_options* opt,
+                              mocap_ba_report* report);
+/* residual vector of S4 at explicit poses (helpers.py:264-276); r float [n_points],
+ * valid uint8 [n_points]; returns the number of valid residuals in *n_valid. HOST pointers. */
+MOCAP_API int  mocap_ba_residuals_host(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points,
+                             const double* R, const double* t, float* r, uint8_t* valid, int* n_valid);
+
+/* page-locked host memory for the *_host entry points */
+MOCAP_API int  mocap_host_alloc(void** out, uint64_t bytes);
+MOCAP_API void mocap_host_free(void* p);
+
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+MOCAP_API uint64_t mocap_launch_count(const mocap_ctx* ctx);
+/* Average device time in ms of the blob-detection kernel over the launches since the
+ * last call with reset != 0, measured with CUDA events on the context's stream when
+ * enabled by mocap_enable_kernel_timing(ctx, 1).  Synchronises the stream. */
+MOCAP_API int  mocap_enable_kernel_timing(mocap_ctx* ctx, int on);
+MOCAP_API int  mocap_detect_kernel_ms(mocap_ctx* ctx, int reset, double* avg_ms, int* n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOCAP_B200_H */

@@ -1,0 +1,413 @@
+// C ABI of libmocap_b200.so (see include/mocap_b200.h for the contract and the
+// reference functions each entry point replaces).
+#include <stdarg.h>
+#include <stdlib.h>
+#include <math.h>
+#include <new>
+#include "common.cuh"
+
+int blob_kernels_init(mocap_ctx* ctx);
+int match_kernels_init(mocap_ctx* ctx);
+
+int mocap_fail(mocap_ctx* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+int ensure_scratch(mocap_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return MOCAP_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_scratch);
+    ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return MOCAP_OK;
+}
+
+
+extern "C" {
+
+const char* mocap_status_string(int status) {
+    switch (status) {
+        case MOCAP_OK: return "ok";
+        case MOCAP_EINVAL: return "invalid argument";
+        case MOCAP_ENODEV: return "no usable CUDA device (libmocap_b200 needs an sm_100 GPU; there is no CPU fallback)";
+        case MOCAP_ECUDA: return "CUDA runtime error";
+        case MOCAP_ENOMEM: return "out of memory";
+        case MOCAP_ESTATE: return "call order error (cameras not set?)";
+        default: return "unknown status";
+    }
+}
+
+void mocap_default_config(mocap_config* cfg, int n_cam, int width, int height) {
+    cfg->device = 0;
+    cfg->n_cam = n_cam;
+    cfg->width = width;
+    cfg->height = height;
+    cfg->max_blobs = 32;
+    cfg->max_segments = 1024;
+    cfg->max_roots = 64;
+    cfg->max_cands = 8;
+    cfg->max_groups = 4096;
+}
+
+const char* mocap_last_error(const mocap_ctx* ctx) { return ctx ? ctx->err : "no context"; }
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int mocap_create(mocap_ctx** out, const mocap_config* cfg) {
+    if (!out || !cfg) return MOCAP_EINVAL;
+    *out = nullptr;
+    if (cfg->n_cam < 1 || cfg->n_cam > MOCAP_MAX_CAM || cfg->width < 16 || cfg->width % MOCAP_SEG_PX != 0 ||
+        cfg->height < 1 || cfg->max_blobs < 1 || cfg->max_blobs > MOCAP_MAX_BLOBS ||
+        !is_pow2(cfg->max_segments) || cfg->max_segments < 64 || cfg->max_segments > 4096 ||
+        cfg->max_roots < 1 || cfg->max_roots > MOCAP_MAX_ROOTS || cfg->max_cands < 1 || cfg->max_cands > MOCAP_MAX_CANDS ||
+        cfg->max_groups < 1 || (long long)cfg->width * cfg->height / MOCAP_SEG_PX > 65535)
+        return MOCAP_EINVAL;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || cfg->device < 0 || cfg->device >= n_dev) {
+        cudaGetLastError();
+        return MOCAP_ENODEV;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return MOCAP_ENODEV;
+    if (prop.major != 10) return MOCAP_ENODEV;        // the fatbin holds sm_100a code only
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return MOCAP_ENODEV;
+
+    mocap_ctx* ctx = new (std::nothrow) mocap_ctx();
+    if (!ctx) return MOCAP_ENOMEM;
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->cfg = *cfg;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->h_tables.n_cam = cfg->n_cam;
+    int st = MOCAP_OK;
+    do {
+        if (cudaMalloc(&ctx->d_tables, sizeof(CameraTables)) != cudaSuccess) { st = MOCAP_ENOMEM; break; }
+        if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { st = MOCAP_ECUDA; break; }
+        for (int k = 0; k < 2 * 64; ++k)
+            if (cudaEventCreate(&ctx->tim_ev[k]) != cudaSuccess) { st = MOCAP_ECUDA; break; }
+        if (st) break;
+        for (int k = 0; k < 2; ++k)
+            if (cudaEventCreateWithFlags(&ctx->stage_free[k], cudaEventDisableTiming) != cudaSuccess) { st = MOCAP_ECUDA; break; }
+        if (st) break;
+        if ((st = blob_kernels_init(ctx)) != MOCAP_OK) break;
+        if ((st = match_kernels_init(ctx)) != MOCAP_OK) break;
+    } while (0);
+    if (st != MOCAP_OK) { mocap_destroy(ctx); return st; }
+    *out = ctx;
+    return MOCAP_OK;
+}
+
+void mocap_destroy(mocap_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->d_tables);
+    cudaFree(ctx->d_seg_count); cudaFree(ctx->d_seg_list);
+    cudaFree(ctx->d_blob_xy); cudaFree(ctx->d_blob_n); cudaFree(ctx->d_img_flags);
+    cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
+    cudaFree(ctx->d_obj); cudaFree(ctx->d_err); cudaFree(ctx->d_nobj); cudaFree(ctx->d_setflags);
+    cudaFree(ctx->d_scratch);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int k = 0; k < 2 * 64; ++k) if (ctx->tim_ev[k]) cudaEventDestroy(ctx->tim_ev[k]);
+    for (int k = 0; k < 2; ++k) if (ctx->stage_free[k]) cudaEventDestroy(ctx->stage_free[k]);
+    delete ctx;
+}
+
+int mocap_set_stream(mocap_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return MOCAP_EINVAL;
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return MOCAP_OK;
+}
+
+// ---- host-side camera tables -------------------------------------------------------------
+static double det3(const double a[3][3]) {
+    return a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+           a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+}
+static double det4(const double m[4][4]) {       // cofactor expansion along row 0, same order as oracle/sfm_shim.py
+    double d = 0.0;
+    for (int j = 0; j < 4; ++j) {
+        double minor[3][3];
+        for (int r = 1; r < 4; ++r) {
+            int cc = 0;
+            for (int c = 0; c < 4; ++c) if (c != j) minor[r - 1][cc++] = m[r][c];
+        }
+        const double term = m[0][j] * det3(minor);
+        d = (j % 2 == 0) ? d + term : d - term;
+    }
+    return d;
+}
+// libmv FundamentalFromProjections (cv.sfm.fundamentalFromProjections, helpers.py:362)
+static void fundamental_from_projections(const double* P1, const double* P2, double* F) {
+    static const int pair[3][2] = {{1, 2}, {2, 0}, {0, 1}};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double m[4][4];
+            for (int c = 0; c < 4; ++c) {
+                m[0][c] = P1[pair[j][0] * 4 + c]; m[1][c] = P1[pair[j][1] * 4 + c];
+                m[2][c] = P2[pair[i][0] * 4 + c]; m[3][c] = P2[pair[i][1] * 4 + c];
+            }
+            F[i * 3 + j] = det4(m);
+        }
+}
+
+int mocap_set_cameras(mocap_ctx* ctx, const double* K, const double* R, const double* t) {
+    if (!ctx || !K || !R || !t) return MOCAP_EINVAL;
+    const int C = ctx->cfg.n_cam;
+    CameraTables& T = ctx->h_tables;
+    for (int c = 0; c < C; ++c) {
+        memcpy(T.R[c], R + 9 * c, 9 * sizeof(double));
+        memcpy(T.t[c], t + 3 * c, 3 * sizeof(double));
+        T.fx[c] = K[9 * c + 0]; T.fy[c] = K[9 * c + 4]; T.cx[c] = K[9 * c + 2]; T.cy[c] = K[9 * c + 5];
+    }
+    for (int k = 0; k < C; ++k)
+        for (int c = 0; c < C; ++c)
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 4; ++j) {
+                    // K_k @ [R_c | t_c] the way a BLAS dgemm micro-kernel sums it (fused multiply-adds over k)
+                    double acc = K[9 * k + 3 * i + 0] * (j < 3 ? R[9 * c + 0 * 3 + j] : t[3 * c + 0]);
+                    acc = fma(K[9 * k + 3 * i + 1], (j < 3 ? R[9 * c + 1 * 3 + j] : t[3 * c + 1]), acc);
+                    acc = fma(K[9 * k + 3 * i + 2], (j < 3 ? R[9 * c + 2 * 3 + j] : t[3 * c + 2]), acc);
+                    T.Pkc[k][c][4 * i + j] = acc;
+                }
+    for (int r = 0; r < C; ++r)
+        for (int c = 0; c < C; ++c) fundamental_from_projections(T.Pkc[r][r], T.Pkc[c][c], T.F[r][c]);
+    T.n_cam = C;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_tables, &T, sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // T lives in pageable memory of the ctx
+    ctx->cameras_set = true;
+    return MOCAP_OK;
+}
+
+int mocap_set_world_transform(mocap_ctx* ctx, const double* M) {
+    if (!ctx) return MOCAP_EINVAL;
+    CameraTables& T = ctx->h_tables;
+    T.use_world = M ? 1 : 0;
+    if (M) memcpy(T.world, M, 16 * sizeof(double));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_tables, &T, sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return MOCAP_OK;
+}
+
+// ---- scratch management ------------------------------------------------------------------
+static int ensure_images(mocap_ctx* ctx, int n_images) {
+    if (n_images <= ctx->cap_images) return MOCAP_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_seg_count); cudaFree(ctx->d_seg_list); cudaFree(ctx->d_blob_xy); cudaFree(ctx->d_blob_n); cudaFree(ctx->d_img_flags);
+    ctx->d_seg_count = nullptr; ctx->d_seg_list = nullptr; ctx->d_blob_xy = nullptr; ctx->d_blob_n = nullptr; ctx->d_img_flags = nullptr;
+    ctx->cap_images = 0;
+    const size_t n = (size_t)n_images;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_seg_count, n * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_seg_list, n * ctx->cfg.max_segments * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_blob_xy, n * ctx->cfg.max_blobs * 2 * sizeof(int32_t)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_blob_n, n * sizeof(int32_t)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_img_flags, n * sizeof(int32_t)));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_seg_count, 0, n * sizeof(uint32_t), ctx->stream));   // kept zero by k_blob_reduce afterwards
+    ctx->cap_images = n_images;
+    return MOCAP_OK;
+}
+
+static int ensure_sets(mocap_ctx* ctx, int n_sets) {
+    if (n_sets <= ctx->cap_sets) return MOCAP_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_obj); cudaFree(ctx->d_err); cudaFree(ctx->d_nobj); cudaFree(ctx->d_setflags);
+    ctx->d_obj = nullptr; ctx->d_err = nullptr; ctx->d_nobj = nullptr; ctx->d_setflags = nullptr; ctx->cap_sets = 0;
+    const size_t n = (size_t)n_sets, R = ctx->cfg.max_roots;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_obj, n * R * 3 * sizeof(double)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_err, n * R * sizeof(double)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_nobj, n * sizeof(int32_t)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_setflags, n * sizeof(int32_t)));
+    ctx->cap_sets = n_sets;
+    return MOCAP_OK;
+}
+
+// ---- S1 ------------------------------------------------------------------------------------
+int mocap_detect_dev(mocap_ctx* ctx, const uint8_t* frames, int n_images, int channels, int threshold,
+                     int32_t* blob_xy, int32_t* blob_n, int64_t* blob_mom, int32_t* img_flags) {
+    if (!ctx) return MOCAP_EINVAL;
+    if (!frames || !blob_xy || !blob_n || n_images < 0 || (channels != 1 && channels != 3))
+        return mocap_fail(ctx, MOCAP_EINVAL, "mocap_detect_dev: bad argument");
+    if ((reinterpret_cast<uintptr_t>(frames) & 15u) != 0)
+        return mocap_fail(ctx, MOCAP_EINVAL, "mocap_detect_dev: frames must be 16-byte aligned");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+    int st = ensure_images(ctx, n_images);
+    if (st) return st;
+    return launch_detect(ctx, frames, n_images, channels, threshold, blob_xy, blob_n, blob_mom, img_flags);
+}
+
+// ---- S2+S3 ---------------------------------------------------------------------------------
+int mocap_match_triangulate_dev(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n, int n_frame_sets,
+                                double* obj, double* err, int32_t* n_obj, int32_t* set_flags, int32_t* chosen) {
+    if (!ctx) return MOCAP_EINVAL;
+    if (!blob_xy || !blob_n || !obj || !err || !n_obj || n_frame_sets < 0)
+        return mocap_fail(ctx, MOCAP_EINVAL, "mocap_match_triangulate_dev: bad argument");
+    if (!ctx->cameras_set) return mocap_fail(ctx, MOCAP_ESTATE, "mocap_set_cameras has not been called");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+    return launch_match(ctx, blob_xy, blob_n, n_frame_sets, obj, err, n_obj, set_flags, chosen);
+}
+
+// ---- S1+S2+S3 ------------------------------------------------------------------------------
+int mocap_pipeline_dev(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets, int channels, int threshold,
+                       double* obj, double* err, int32_t* n_obj, int32_t* set_flags) {
+    if (!ctx) return MOCAP_EINVAL;
+    if (!frames || !obj || !err || !n_obj || n_frame_sets < 0 || (channels != 1 && channels != 3))
+        return mocap_fail(ctx, MOCAP_EINVAL, "mocap_pipeline_dev: bad argument");
+    if (!ctx->cameras_set) return mocap_fail(ctx, MOCAP_ESTATE, "mocap_set_cameras has not been called");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+    const int C = ctx->cfg.n_cam;
+    const size_t set_bytes = (size_t)C * ctx->cfg.width * ctx->cfg.height * channels;
+    const int chunk = 4096;                       // frame-sets per launch group: bounds the segment-list scratch
+    int st = ensure_images(ctx, (n_frame_sets < chunk ? n_frame_sets : chunk) * C);
+    if (st) return st;
+    for (int s0 = 0; s0 < n_frame_sets; s0 += chunk) {
+        const int ns = (n_frame_sets - s0 < chunk) ? n_frame_sets - s0 : chunk;
+        st = launch_detect(ctx, frames + (size_t)s0 * set_bytes, ns * C, channels, threshold,
+                           ctx->d_blob_xy, ctx->d_blob_n, nullptr, ctx->d_img_flags);
+        if (st) return st;
+        st = launch_match(ctx, ctx->d_blob_xy, ctx->d_blob_n, ns, obj + (size_t)s0 * ctx->cfg.max_roots * 3,
+                          err + (size_t)s0 * ctx->cfg.max_roots, n_obj + s0, set_flags ? set_flags + s0 : nullptr, nullptr);
+        if (st) return st;
+    }
+    return MOCAP_OK;
+}
+
+int mocap_pipeline_host(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets, int channels, int threshold,
+                        double* obj, double* err, int32_t* n_obj, int32_t* set_flags) {
+    if (!ctx) return MOCAP_EINVAL;
+    if (!frames || !obj || !err || !n_obj || n_frame_sets < 0 || (channels != 1 && channels != 3))
+        return mocap_fail(ctx, MOCAP_EINVAL, "mocap_pipeline_host: bad argument");
+    if (!ctx->cameras_set) return mocap_fail(ctx, MOCAP_ESTATE, "mocap_set_cameras has not been called");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+    const int C = ctx->cfg.n_cam, RM = ctx->cfg.max_roots;
+    const size_t set_bytes = (size_t)C * ctx->cfg.width * ctx->cfg.height * channels;
+    int chunk = (int)((size_t)(256u << 20) / set_bytes);      // ~256 MB per staging buffer
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_frame_sets) chunk = n_frame_sets > 0 ? n_frame_sets : 1;
+    const size_t need = (size_t)chunk * set_bytes;
+    if (need > ctx->stage_bytes) {
+        CUDA_TRY(ctx, cudaDeviceSynchronize());
+        for (int k = 0; k < 2; ++k) { cudaFree(ctx->d_stage[k]); ctx->d_stage[k] = nullptr; }
+        ctx->stage_bytes = 0;
+        for (int k = 0; k < 2; ++k) CUDA_TRY(ctx, cudaMalloc(&ctx->d_stage[k], need));
+        ctx->stage_bytes = need;
+    }
+    int st = ensure_sets(ctx, n_frame_sets);
+    if (st) return st;
+    st = ensure_images(ctx, chunk * C);
+    if (st) return st;
+    cudaEvent_t copied;
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+    int k = 0, n_chunks = 0;
+    for (int s0 = 0; s0 < n_frame_sets; s0 += chunk, k ^= 1, ++n_chunks) {
+        const int ns = (n_frame_sets - s0 < chunk) ? n_frame_sets - s0 : chunk;
+        if (n_chunks >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[k], 0));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[k], frames + (size_t)s0 * set_bytes, (size_t)ns * set_bytes,
+                                      cudaMemcpyHostToDevice, ctx->copy_stream));
+        CUDA_TRY(ctx, cudaEventRecord(copied, ctx->copy_stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, copied, 0));
+        st = launch_detect(ctx, ctx->d_stage[k], ns * C, channels, threshold, ctx->d_blob_xy, ctx->d_blob_n, nullptr, ctx->d_img_flags);
+        if (st) break;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->stage_free[k], ctx->stream));
+        st = launch_match(ctx, ctx->d_blob_xy, ctx->d_blob_n, ns, ctx->d_obj + (size_t)s0 * RM * 3, ctx->d_err + (size_t)s0 * RM,
+                          ctx->d_nobj + s0, ctx->d_setflags + s0, nullptr);
+        if (st) break;
+    }
+    cudaEventDestroy(copied);
+    if (st) return st;
+    const size_t n = (size_t)n_frame_sets;
+    CUDA_TRY(ctx, cudaMemcpyAsync(obj, ctx->d_obj, n * RM * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(err, ctx->d_err, n * RM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(n_obj, ctx->d_nobj, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (set_flags) CUDA_TRY(ctx, cudaMemcpyAsync(set_flags, ctx->d_setflags, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return MOCAP_OK;
+}
+
+// ---- S3 on explicit correspondences ----------------------------------------------------------
+int mocap_triangulate_dev(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points,
+                          double* X, double* err, uint8_t* valid) {
+    if (!ctx) return MOCAP_EINVAL;
+    if (!obs || !mask || !X || n_points < 0) return mocap_fail(ctx, MOCAP_EINVAL, "mocap_triangulate_dev: bad argument");
+    if (!ctx->cameras_set) return mocap_fail(ctx, MOCAP_ESTATE, "mocap_set_cameras has not been called");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+    return launch_triangulate(ctx, obs, mask, n_points, nullptr, X, err, valid);
+}
+
+static int tri_host_common(mocap_ctx* ctx, const double* obs, const uint8_t* mask, const double* X_in, int n_points,
+                           double* X, double* err, uint8_t* valid) {
+    if (!ctx) return MOCAP_EINVAL;
+    if (!obs || !mask || n_points < 0) return mocap_fail(ctx, MOCAP_EINVAL, "triangulate: bad argument");
+    if (!ctx->cameras_set) return mocap_fail(ctx, MOCAP_ESTATE, "mocap_set_cameras has not been called");
+    if (n_points == 0) return MOCAP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+    const int C = ctx->cfg.n_cam;
+    const size_t n = (size_t)n_points;
+    const size_t b_obs = n * C * 2 * sizeof(double), b_X = n * 3 * sizeof(double), b_err = n * sizeof(double);
+    const size_t b_mask = (n * C + 15) & ~(size_t)15, b_valid = (n + 15) & ~(size_t)15;
+    int st = ensure_scratch(ctx, b_obs + 2 * b_X + b_err + b_mask + b_valid);
+    if (st) return st;
+    unsigned char* p = static_cast<unsigned char*>(ctx->d_scratch);
+    double* d_obs = reinterpret_cast<double*>(p); p += b_obs;
+    double* d_X = reinterpret_cast<double*>(p); p += b_X;
+    double* d_Xin = reinterpret_cast<double*>(p); p += b_X;
+    double* d_err = reinterpret_cast<double*>(p); p += b_err;
+    uint8_t* d_mask = p; p += b_mask;
+    uint8_t* d_valid = p;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_obs, obs, b_obs, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_mask, mask, n * C, cudaMemcpyHostToDevice, ctx->stream));
+    if (X_in) CUDA_TRY(ctx, cudaMemcpyAsync(d_Xin, X_in, b_X, cudaMemcpyHostToDevice, ctx->stream));
+    st = launch_triangulate(ctx, d_obs, d_mask, n_points, X_in ? d_Xin : nullptr, d_X, d_err, d_valid);
+    if (st) return st;
+    if (X) CUDA_TRY(ctx, cudaMemcpyAsync(X, d_X, b_X, cudaMemcpyDeviceToHost, ctx->stream));
+    if (err) CUDA_TRY(ctx, cudaMemcpyAsync(err, d_err, b_err, cudaMemcpyDeviceToHost, ctx->stream));
+    if (valid) CUDA_TRY(ctx, cudaMemcpyAsync(valid, d_valid, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return MOCAP_OK;
+}
+
+int mocap_triangulate_host(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points,
+                           double* X, double* err, uint8_t* valid) {
+    if (ctx && !X) return mocap_fail(ctx, MOCAP_EINVAL, "mocap_triangulate_host: X is NULL");
+    return tri_host_common(ctx, obs, mask, nullptr, n_points, X, err, valid);
+}
+
+int mocap_reprojection_errors_host(mocap_ctx* ctx, const double* obs, const uint8_t* mask, const double* X,
+                                   int n_points, double* err, uint8_t* valid) {
+    if (ctx && (!X || !err)) return mocap_fail(ctx, MOCAP_EINVAL, "mocap_reprojection_errors_host: NULL argument");
+    return tri_host_common(ctx, obs, mask, X, n_points, nullptr, err, valid);
+}
+
+// ---- misc ------------------------------------------------------------------------------------
+int mocap_host_alloc(void** out, uint64_t bytes) {
+    if (!out) return MOCAP_EINVAL;
+    *out = nullptr;
+    if (cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return MOCAP_ENOMEM; }
+    return MOCAP_OK;
+}
+void mocap_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+uint64_t mocap_launch_count(const mocap_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mocap_enable_kernel_timing(mocap_ctx* ctx, int on) {
+    if (!ctx) return MOCAP_EINVAL;
+    ctx->timing_on = on ? 1 : 0;
+    return MOCAP_OK;
+}
+int mocap_detect_kernel_ms(mocap_ctx* ctx, int reset, double* avg_ms, int* n_launches) {
+    if (!ctx) return MOCAP_EINVAL;
+    const int st = timing_flush(ctx);
+    if (st) return st;
+    if (avg_ms) *avg_ms = ctx->detect_ms_n ? ctx->detect_ms_sum / ctx->detect_ms_n : 0.0;
+    if (n_launches) *n_launches = ctx->detect_ms_n;
+    if (reset) { ctx->detect_ms_sum = 0.0; ctx->detect_ms_n = 0; }
+    return MOCAP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// Shared declarations of libmocap_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/mocap_b200.h"
+
+#define MOCAP_MAX_CAM        16
+#define MOCAP_MAX_BLOBS      64
+#define MOCAP_MAX_ROOTS      128
+#define MOCAP_MAX_CANDS      16
+#define MOCAP_ACC_CAP        256     // blobs accumulated per image before max_blobs truncation
+#define MOCAP_SEG_PX         16      // pixels per threshold segment (one 128-bit load of 1-channel data)
+
+// Camera tables, device resident (built on the host by mocap_set_cameras).
+struct CameraTables {
+    double Pkc[MOCAP_MAX_CAM][MOCAP_MAX_CAM][12];  // Pkc[k][c] = K_k [R_c|t_c]  (helpers.py:305-308 uses K of the k-th PRESENT view)
+    double F[MOCAP_MAX_CAM][MOCAP_MAX_CAM][9];     // F[r][c]: line in camera c of a point in camera r (helpers.py:362)
+    double R[MOCAP_MAX_CAM][9];
+    double t[MOCAP_MAX_CAM][3];
+    double fx[MOCAP_MAX_CAM], fy[MOCAP_MAX_CAM], cx[MOCAP_MAX_CAM], cy[MOCAP_MAX_CAM];  // cv.projectPoints reads these four of K
+    double world[16];                              // to_world_coords_matrix (helpers.py:99)
+    int    use_world;
+    int    n_cam;
+};
+
+struct mocap_ctx {
+    mocap_config cfg;
+    cudaStream_t stream;
+    cudaStream_t copy_stream;
+    char         err[512];
+    bool         cameras_set;
+    CameraTables* d_tables;
+    CameraTables  h_tables;
+    // detection scratch, sized for cap_images
+    int       cap_images;
+    uint32_t* d_seg_count;
+    uint32_t* d_seg_list;
+    int32_t*  d_blob_xy;
+    int32_t*  d_blob_n;
+    int32_t*  d_img_flags;
+    // host-path staging
+    uint8_t*  d_stage[2];
+    size_t    stage_bytes;
+    cudaEvent_t stage_free[2];
+    double*   d_obj; double* d_err; int32_t* d_nobj; int32_t* d_setflags;
+    int       cap_sets;
+    // generic scratch for the *_host triangulation / BA entry points
+    void*     d_scratch; size_t scratch_bytes;
+    // accounting
+    uint64_t  launches;
+    int       timing_on;
+    cudaEvent_t tim_ev[2 * 64];   // pairs bracketing k_threshold_segments, resolved lazily
+    int       tim_used;
+    double    detect_ms_sum;
+    int       detect_ms_n;
+    int       num_sms;
+};
+
+int mocap_fail(mocap_ctx* ctx, int code, const char* fmt, ...);
+#define CUDA_TRY(ctx, call)                                                              \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess)                                                          \
+            return mocap_fail((ctx), MOCAP_ECUDA, "%s failed: %s (%s:%d)", #call,        \
+                              cudaGetErrorString(e__), __FILE__, __LINE__);              \
+    } while (0)
+
+// kernel launchers (each returns a MOCAP_* status; all enqueue on ctx->stream)
+int launch_detect(mocap_ctx* ctx, const uint8_t* frames, int n_images, int channels, int threshold,
+                  int32_t* blob_xy, int32_t* blob_n, int64_t* blob_mom, int32_t* img_flags);
+int launch_match(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n, int n_sets,
+                 double* obj, double* err, int32_t* n_obj, int32_t* set_flags, int32_t* chosen);
+int launch_triangulate(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points,
+                       const double* X_in, double* X, double* err, uint8_t* valid);
+size_t blob_reduce_smem_bytes(int max_segments);
+size_t match_smem_bytes(const mocap_config& cfg, int warps);
+int ensure_scratch(mocap_ctx* ctx, size_t bytes);
+int timing_flush(mocap_ctx* ctx);

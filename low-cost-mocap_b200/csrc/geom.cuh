@@ -1,0 +1,175 @@
+// Per-point geometry of S3 / reprojection error, usable from device and (for the
+// host-side unit checks in tests/hostcheck) from host code.
+//
+// Reference semantics restated here (computer_code/api/helpers.py):
+//   triangulate_point  :293-327  rows y*P[2]-P[1], P[0]-x*P[2]; B = A^T A; SVD(B); X = Vh[3,:3]/Vh[3,3]
+//   calculate_reprojection_error :214-241  X -> float32, cv.projectPoints (double math,
+//        float32 result), mean of squared pixel residuals in float64
+#pragma once
+#include <math.h>
+
+#if defined(__CUDA_ARCH__)
+#define GEOM_HD __host__ __device__ __forceinline__
+// exact (non-fused) double ops where the reference's rounding sequence must be kept
+#define DMUL(a, b) __dmul_rn((a), (b))
+#define DADD(a, b) __dadd_rn((a), (b))
+#define DSUB(a, b) __dsub_rn((a), (b))
+#define DFMA(a, b, c) fma((a), (b), (c))
+#elif defined(__CUDACC__)
+#define GEOM_HD __host__ __device__ __forceinline__
+#define DMUL(a, b) ((a) * (b))
+#define DADD(a, b) ((a) + (b))
+#define DSUB(a, b) ((a) - (b))
+#define DFMA(a, b, c) fma((a), (b), (c))
+#else
+#define GEOM_HD static inline
+#define DMUL(a, b) ((a) * (b))
+#define DADD(a, b) ((a) + (b))
+#define DSUB(a, b) ((a) - (b))
+#define DFMA(a, b, c) fma((a), (b), (c))
+#endif
+
+// Upper triangle of the 4x4 normal matrix, order 00 01 02 03 11 12 13 22 23 33.
+struct Sym4 { double v[10]; };
+
+GEOM_HD void sym4_zero(Sym4& B) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) B.v[i] = 0.0;
+}
+
+GEOM_HD void sym4_add_row(Sym4& B, double r0, double r1, double r2, double r3) {
+    B.v[0] = DFMA(r0, r0, B.v[0]); B.v[1] = DFMA(r0, r1, B.v[1]); B.v[2] = DFMA(r0, r2, B.v[2]); B.v[3] = DFMA(r0, r3, B.v[3]);
+    B.v[4] = DFMA(r1, r1, B.v[4]); B.v[5] = DFMA(r1, r2, B.v[5]); B.v[6] = DFMA(r1, r3, B.v[6]);
+    B.v[7] = DFMA(r2, r2, B.v[7]); B.v[8] = DFMA(r2, r3, B.v[8]);
+    B.v[9] = DFMA(r3, r3, B.v[9]);
+}
+
+// One view of the DLT system (helpers.py:314-316).  P: 3x4 row-major.  The A entries are
+// formed with separately rounded multiply and subtract, exactly as numpy forms them.
+GEOM_HD void dlt_add_view(Sym4& B, const double* __restrict__ P, double x, double y) {
+    const double a0 = DSUB(DMUL(y, P[8]), P[4]), a1 = DSUB(DMUL(y, P[9]), P[5]);
+    const double a2 = DSUB(DMUL(y, P[10]), P[6]), a3 = DSUB(DMUL(y, P[11]), P[7]);
+    sym4_add_row(B, a0, a1, a2, a3);
+    const double b0 = DSUB(P[0], DMUL(x, P[8])), b1 = DSUB(P[1], DMUL(x, P[9]));
+    const double b2 = DSUB(P[2], DMUL(x, P[10])), b3 = DSUB(P[3], DMUL(x, P[11]));
+    sym4_add_row(B, b0, b1, b2, b3);
+}
+
+#define JROT(p, q)                                                                       \
+    {                                                                                     \
+        const double apq = a[p][q];                                                       \
+        if (apq != 0.0) {                                                                 \
+            const double g100 = 100.0 * fabs(apq);                                        \
+            if (sweep > 3 && fabs(a[p][p]) + g100 == fabs(a[p][p]) &&                     \
+                fabs(a[q][q]) + g100 == fabs(a[q][q])) {                                  \
+                a[p][q] = 0.0;                                                            \
+            } else {                                                                      \
+                const double hdiff = a[q][q] - a[p][p];                                   \
+                double tt;                                                                \
+                if (fabs(hdiff) + g100 == fabs(hdiff)) {                                  \
+                    tt = apq / hdiff;                                                     \
+                } else {                                                                  \
+                    const double theta = 0.5 * hdiff / apq;                               \
+                    tt = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));                 \
+                    if (theta < 0.0) tt = -tt;                                            \
+                }                                                                         \
+                const double cc = 1.0 / sqrt(1.0 + tt * tt);                              \
+                const double ss = tt * cc;                                                \
+                const double tau = ss / (1.0 + cc);                                       \
+                const double hh = tt * apq;                                               \
+                a[p][p] -= hh;                                                            \
+                a[q][q] += hh;                                                            \
+                a[p][q] = 0.0;                                                            \
+                _Pragma("unroll") for (int r = 0; r < 4; ++r) {                           \
+                    if (r != p && r != q) {                                               \
+                        const double gg = (r < p) ? a[r][p] : a[p][r];                    \
+                        const double h2 = (r < q) ? a[r][q] : a[q][r];                    \
+                        const double ng = gg - ss * (h2 + gg * tau);                      \
+                        const double nh = h2 + ss * (gg - h2 * tau);                      \
+                        if (r < p) a[r][p] = ng; else a[p][r] = ng;                       \
+                        if (r < q) a[r][q] = nh; else a[q][r] = nh;                       \
+                    }                                                                     \
+                }                                                                         \
+                _Pragma("unroll") for (int r = 0; r < 4; ++r) {                           \
+                    const double gg = v[r][p], h2 = v[r][q];                              \
+                    v[r][p] = gg - ss * (h2 + gg * tau);                                  \
+                    v[r][q] = h2 + ss * (gg - h2 * tau);                                  \
+                }                                                                         \
+            }                                                                             \
+        }                                                                                 \
+    }
+
+// Null-space direction of the symmetric 4x4 normal matrix: the eigenvector of the
+// eigenvalue of smallest magnitude (== last right singular vector, Vh[3] of
+// scipy.linalg.svd(B), helpers.py:320-321, up to sign -- the sign cancels in X).
+// Cyclic Jacobi in registers: small eigenvalues of a positive matrix come out with
+// high relative accuracy, which the squared conditioning of A^T A needs.
+GEOM_HD void sym4_null_vector(const Sym4& B, double out[4]) {
+    double a[4][4], v[4][4];
+    a[0][0] = B.v[0]; a[0][1] = B.v[1]; a[0][2] = B.v[2]; a[0][3] = B.v[3];
+    a[1][1] = B.v[4]; a[1][2] = B.v[5]; a[1][3] = B.v[6];
+    a[2][2] = B.v[7]; a[2][3] = B.v[8];
+    a[3][3] = B.v[9];
+    a[1][0] = a[2][0] = a[2][1] = a[3][0] = a[3][1] = a[3][2] = 0.0;   // only the upper triangle is used
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[r][c] = (r == c) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[0][3]) + fabs(a[1][2]) + fabs(a[1][3]) + fabs(a[2][3]);
+        if (off == 0.0) break;
+        JROT(0, 1) JROT(0, 2) JROT(0, 3) JROT(1, 2) JROT(1, 3) JROT(2, 3)
+    }
+    int best = 0;
+    double bv = fabs(a[0][0]);
+    if (fabs(a[1][1]) < bv) { bv = fabs(a[1][1]); best = 1; }
+    if (fabs(a[2][2]) < bv) { bv = fabs(a[2][2]); best = 2; }
+    if (fabs(a[3][3]) < bv) { bv = fabs(a[3][3]); best = 3; }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        out[r] = best == 0 ? v[r][0] : best == 1 ? v[r][1] : best == 2 ? v[r][2] : v[r][3];
+}
+
+GEOM_HD void dlt_solve(const Sym4& B, double X[3]) {
+    double n[4];
+    sym4_null_vector(B, n);
+    X[0] = n[0] / n[3]; X[1] = n[1] / n[3]; X[2] = n[2] / n[3];     // helpers.py:321
+}
+
+// cv.projectPoints with zero distortion on a float32 point (helpers.py:231-238): the
+// float32-rounded point is widened, x = R X + t summed left to right, z -> 1/z (1 if
+// z == 0), u = x*fx + cx, result stored as float32.  Verified bit-exact against cv2 4.13.
+GEOM_HD void project_like_cv(const double* __restrict__ R, const double* __restrict__ t,
+                             double fx, double fy, double cx, double cy,
+                             const double X[3], float& u, float& v) {
+    const double Xs = (double)(float)X[0], Ys = (double)(float)X[1], Zs = (double)(float)X[2];
+    double x = DADD(DADD(DADD(DMUL(R[0], Xs), DMUL(R[1], Ys)), DMUL(R[2], Zs)), t[0]);
+    double y = DADD(DADD(DADD(DMUL(R[3], Xs), DMUL(R[4], Ys)), DMUL(R[5], Zs)), t[1]);
+    double z = DADD(DADD(DADD(DMUL(R[6], Xs), DMUL(R[7], Ys)), DMUL(R[8], Zs)), t[2]);
+    z = (z != 0.0) ? 1.0 / z : 1.0;
+    x = DMUL(x, z);
+    y = DMUL(y, z);
+    u = (float)DADD(DMUL(x, fx), cx);
+    v = (float)DADD(DMUL(y, fy), cy);
+}
+
+// numpy's reduction of n squared residuals (n = 2 * views <= 32) followed by / n.
+//  pairwise == false: left fold (object-dtype arrays: any group that contains a None view)
+//  pairwise == true : np.add.reduce on float64, blocked 8-accumulator form for 8 <= n < 128
+GEOM_HD double mean_like_numpy(const double* sq, int n, bool pairwise) {
+    double res;
+    if (!pairwise || n < 8) {
+        res = 0.0;
+        if (pairwise) { res = sq[0]; for (int i = 1; i < n; ++i) res = DADD(res, sq[i]); }
+        else { for (int i = 0; i < n; ++i) res = DADD(res, sq[i]); }
+    } else {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = sq[j];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] = DADD(r[j], sq[i + j]);
+        res = DADD(DADD(DADD(r[0], r[1]), DADD(r[2], r[3])), DADD(DADD(r[4], r[5]), DADD(r[6], r[7])));
+        for (; i < n; ++i) res = DADD(res, sq[i]);
+    }
+    return res / (double)n;
+}

@@ -1,0 +1,322 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the committed golden vectors
+written by the real reference, against the oracle port on seeded inputs, and -- at BASELINE
+sizes -- through size-independent properties.  Run with ``-m gpu`` on a B200."""
+import importlib
+
+import numpy as np
+import pytest
+
+from tests.util import load_golden, poses_from, obs_from, as3
+
+pytestmark = pytest.mark.gpu
+
+pkg = importlib.import_module("low-cost-mocap_b200")
+synth = pkg.synth
+
+PIPE_CASES = ["pipe_c2_m1", "pipe_c4_m4", "pipe_c8_m16"]
+X_TOL = 1e-7          # pose units; BASELINE north_star: 1e-4 mm with poses in metres
+ERR_RTOL = 1e-9       # reprojection errors are float32-quantised upstream; expected bit-equal
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch
+
+
+def _ctx(C, **kw):
+    return pkg.MocapContext(C, 640, 480, **kw)
+
+
+# ------------------------------------------------------------------------------------------ S1
+@pytest.mark.parametrize("name", PIPE_CASES + ["blobs_irregular"])
+def test_detect_exact_vs_reference_golden(torch, name):
+    z = load_golden(name)
+    frames = z["frames"]
+    B, C = frames.shape[:2]
+    ctx = _ctx(C, max_blobs=64)
+    d = ctx.detect(torch.from_numpy(frames).cuda(), want_moments=True)
+    n = d["n"].cpu().numpy().reshape(B, C)
+    xy = d["xy"].cpu().numpy().reshape(B, C, 64, 2)
+    assert (d["flags"].cpu().numpy() == 0).all()
+    assert np.array_equal(n, z["blob_n"])                       # exact count
+    for b in range(B):
+        for c in range(C):
+            k = n[b, c]
+            assert np.array_equal(xy[b, c, :k], z["blob_xy"][b, c, :k]), (b, c)   # exact centres, exact order
+
+
+def test_detect_pixel_counts_and_moments_vs_cv2(torch):
+    """Auxiliary checksum: per-blob pixel count == cv2.connectedComponentsWithStats
+    (8-connectivity), and A2/SX6/SY6 == the integers cv.moments accumulates for the contour."""
+    import cv2
+    z = load_golden("blobs_irregular")
+    frames = z["frames"][:, 0]
+    ctx = _ctx(1, max_blobs=64)
+    d = ctx.detect(torch.from_numpy(frames).cuda(), want_moments=True)
+    n = d["n"].cpu().numpy(); mom = d["mom"].cpu().numpy()
+    for f in range(len(frames)):
+        binary = (frames[f] > 51).astype(np.uint8)
+        contours, _ = cv2.findContours(binary * 255, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+        ncc, lab, stats, _ = cv2.connectedComponentsWithStats(binary, connectivity=8)
+        kept = []
+        for cnt in contours:
+            m = cv2.moments(cnt)
+            if m["m00"] != 0:
+                x0, y0 = cnt[0, 0]
+                kept.append((round(m["m00"] * 2), round(m["m10"] * 6), round(m["m01"] * 6), stats[lab[y0, x0], cv2.CC_STAT_AREA]))
+        assert n[f] == len(kept)
+        for i, ref in enumerate(kept):
+            assert tuple(int(v) for v in mom[f, i]) == ref, (f, i)
+
+
+def test_detect_three_channel_layout_matches_oracle(torch):
+    """The drop-in layout (HxWx3, helpers.py:143) incl. cvtColor's fixed-point grey on unequal channels."""
+    from oracle.ref_port import RefPort
+    rng = np.random.default_rng(9)
+    frames, _, _, _ = synth.make_frame_pool(2, 5, 3, seed=21)
+    imgs = []
+    for f in frames.reshape(-1, 480, 640):
+        img = as3(f)
+        img[..., 0] = np.clip(img[..., 0].astype(int) + rng.integers(-30, 30, size=f.shape), 0, 255)
+        img[..., 2] = np.clip(img[..., 2].astype(int) + rng.integers(-30, 30, size=f.shape), 0, 255)
+        imgs.append(img)
+    imgs = np.stack(imgs)
+    ctx = _ctx(1, max_blobs=64)
+    d = ctx.detect(torch.from_numpy(imgs).cuda())
+    port = RefPort([np.eye(3)])
+    for i, img in enumerate(imgs):
+        ref = [p for p in port.find_dot(img.copy()) if p[0] is not None]
+        k = int(d["n"][i])
+        assert d["xy"][i, :k].cpu().numpy().tolist() == ref
+
+
+@pytest.mark.parametrize("threshold", [0, 1, 50, 51, 52, 127, 128, 129, 200, 254, 255])
+def test_threshold_is_strictly_greater(torch, threshold):
+    """pix > threshold for every byte value (the SWAR compare has two regimes around 128)."""
+    img = np.zeros((480, 640), np.uint8)
+    for v in range(256):                       # 256 isolated 2x2 squares, one per grey value
+        y, x = 8 + 12 * (v // 32), 8 + 12 * (v % 32)
+        img[y:y + 2, x:x + 2] = v
+    ctx = _ctx(1, max_blobs=64, max_segments=1024)
+    d = ctx.detect(torch.from_numpy(img[None]).cuda(), threshold=threshold, want_moments=True)
+    expect = 255 - threshold
+    n = int(d["n"][0]); flags = int(d["flags"][0])
+    assert (n == min(expect, 64)) and ((flags & 2) != 0) == (expect > 64)
+
+
+def test_detect_edge_cases(torch):
+    ctx = _ctx(1, max_blobs=8, max_segments=64)
+    imgs = np.zeros((6, 480, 640), np.uint8)
+    imgs[1, 100, 100] = 255                                  # single pixel: zero polygon area -> dropped
+    imgs[2, 0:3, 0:3] = 255; imgs[2, 477:480, 637:640] = 255  # blobs touching the image corners
+    imgs[3, 10:12, 14:18] = 255                              # blob straddling a 16-px segment boundary
+    imgs[4, :, :] = 255                                      # everything set: segment overflow must be flagged
+    for k in range(12):                                      # 12 blobs > max_blobs = 8
+        imgs[5, 20 + 10 * k: 23 + 10 * k, 50:53] = 255
+    d = ctx.detect(torch.from_numpy(imgs).cuda())
+    n = d["n"].cpu().numpy(); fl = d["flags"].cpu().numpy(); xy = d["xy"].cpu().numpy()
+    assert n[0] == 0 and fl[0] == 0
+    assert n[1] == 0 and fl[1] == 0
+    assert n[2] == 2 and xy[2, 0].tolist() == [638, 478] and xy[2, 1].tolist() == [1, 1]
+    assert n[3] == 1 and xy[3, 0].tolist() == [15, 10]
+    assert n[4] == 0 and (fl[4] & 1)
+    assert n[5] == 8 and (fl[5] & 2)
+    assert xy[5, 0].tolist() == [51, 131]                    # reverse raster order: bottom-most blob first
+    # the batch after an overflow must be clean again (segment counters are self-resetting)
+    d2 = ctx.detect(torch.from_numpy(imgs[:4]).cuda())
+    assert d2["n"].cpu().numpy().tolist() == [0, 0, 2, 1]
+
+
+# --------------------------------------------------------------------------------------- S2 + S3
+@pytest.mark.parametrize("name", PIPE_CASES)
+def test_match_triangulate_vs_reference_golden(torch, name):
+    z = load_golden(name)
+    C = int(z["C"]); B = z["blob_n"].shape[0]
+    ctx = _ctx(C, max_blobs=64, max_roots=128)
+    ctx.set_cameras([z["K"]] * C, poses_from(z))
+    xy = torch.from_numpy(z["blob_xy"].reshape(B * C, 64, 2)).cuda()
+    n = torch.from_numpy(z["blob_n"].reshape(B * C)).cuda()
+    d = ctx.match_triangulate(xy, n)
+    k = d["n"].cpu().numpy()
+    assert np.array_equal(k, z["nroot"])                      # same number of kept roots
+    assert (d["flags"].cpu().numpy() == 0).all()
+    obj = d["obj"].cpu().numpy(); err = d["err"].cpu().numpy()
+    worst = 0.0
+    for b in range(B):
+        worst = max(worst, np.abs(obj[b, :k[b]] - z["obj"][b, :k[b]]).max())
+        assert np.allclose(err[b, :k[b]], z["err"][b, :k[b]], rtol=ERR_RTOL, atol=1e-12)
+    assert worst <= X_TOL, worst
+
+
+@pytest.mark.parametrize("name", PIPE_CASES)
+def test_full_pipeline_from_pixels_vs_reference_golden(torch, name):
+    z = load_golden(name)
+    C = int(z["C"]); B = z["blob_n"].shape[0]
+    ctx = _ctx(C, max_blobs=64, max_roots=128)
+    ctx.set_cameras([z["K"]] * C, poses_from(z))
+    out = ctx.pipeline(torch.from_numpy(z["frames"]).cuda())
+    k = out["n"].cpu().numpy()
+    assert np.array_equal(k, z["nroot"])
+    obj = out["obj"].cpu().numpy()
+    for b in range(B):
+        assert np.abs(obj[b, :k[b]] - z["obj"][b, :k[b]]).max() <= X_TOL
+    # host-buffer entry point gives the same bits as the device entry point
+    host = ctx.pipeline_host(torch.from_numpy(z["frames"]))
+    assert np.array_equal(host["n"].numpy(), k)
+    for b in range(B):
+        assert np.array_equal(host["obj"].numpy()[b, :k[b]], obj[b, :k[b]])
+
+
+@pytest.mark.parametrize("name", ["tri_c4", "tri_c8", "tri_c16"])
+def test_triangulate_points_vs_reference_golden(torch, name):
+    z = load_golden(name)
+    C = z["R"].shape[0]
+    ctx = _ctx(C)
+    ctx.set_cameras([z["K"]] * C, poses_from(z))
+    X, err, valid = ctx.triangulate(z["obs"], z["mask"])
+    assert valid.all()
+    assert np.abs(X - z["X"]).max() <= X_TOL
+    assert np.allclose(err, z["err"], rtol=ERR_RTOL, atol=1e-12)
+    e2, v2 = ctx.reprojection_errors(z["obs"], z["mask"], z["X"])
+    assert np.allclose(e2, z["err"], rtol=ERR_RTOL, atol=1e-12)
+
+
+def test_matcher_edge_cases_vs_oracle(torch):
+    """Empty cameras, camera 0 empty (all roots born later), a lone view, ragged counts."""
+    from oracle.ref_port import RefPort
+    C = 4
+    poses, K = synth.make_rig(C)
+    port = RefPort([K] * C)
+    ctx = _ctx(C, max_blobs=16, max_roots=32)
+    ctx.set_cameras([K] * C, poses)
+    rng = np.random.default_rng(3)
+    pts3 = rng.uniform(-0.4, 0.4, size=(5, 3)) + np.array([0, 0, 3.0])
+    proj = [[list(map(int, synth.project(pts3[i:i + 1], p, K)[0])) for i in range(5)] for p in poses]
+    cases = [
+        [proj[0], proj[1], proj[2], proj[3]],
+        [[], proj[1], proj[2], proj[3]],                      # no roots from camera 0
+        [proj[0], [], [], []],                                # single views only -> nothing
+        [proj[0][:2], proj[1][:5], [], proj[3][:1]],          # ragged
+        [[], [], [], proj[3]],
+        [proj[0], proj[1][::-1], proj[2][2:] + proj[2][:2], proj[3]],   # permuted blob order
+    ]
+    MB = 16
+    xy = np.zeros((len(cases), C, MB, 2), np.int32); n = np.zeros((len(cases), C), np.int32)
+    for i, case in enumerate(cases):
+        for c in range(C):
+            n[i, c] = len(case[c])
+            if case[c]:
+                xy[i, c, :len(case[c])] = case[c]
+    d = ctx.match_triangulate(torch.from_numpy(xy.reshape(-1, MB, 2)).cuda(), torch.from_numpy(n.reshape(-1)).cuda(), want_chosen=True)
+    for i, case in enumerate(cases):
+        e, o, chosen = port.match_and_triangulate([[list(p) for p in cam] for cam in case], poses)
+        k = int(d["n"][i])
+        assert k == len(e), i
+        if k:
+            assert np.abs(d["obj"][i, :k].cpu().numpy() - np.asarray(o, dtype=np.float64)).max() <= X_TOL
+            assert np.allclose(d["err"][i, :k].cpu().numpy(), e, rtol=ERR_RTOL, atol=1e-12)
+            ch = d["chosen"][i, :k].cpu().numpy()
+            for r in range(k):                                # identical selected correspondences
+                for c in range(C):
+                    want = chosen[r][c]
+                    got = None if ch[r, c] < 0 else case[c][ch[r, c]]
+                    assert (want[0] is None and got is None) or (got is not None and list(want) == list(got))
+
+
+def test_mirror_functions_match_oracle(torch):
+    """The reference-signature layer (api.py) against the oracle port, argument for argument."""
+    from oracle.ref_port import RefPort
+    C = 3
+    obs, poses, K, _ = synth.make_tracks(C, 25, seed=4, missing_frac=0.3)
+    port = RefPort([K] * C)
+    s = pkg.MocapSession([K] * C)
+    X = pkg.triangulate_points(obs, poses, session=s)
+    Xr = port.triangulate_many(obs, poses)
+    for a, b in zip(X, Xr):
+        assert (a[0] is None) == (b[0] is None)
+        if a[0] is not None:
+            assert np.abs(np.asarray(a, float) - np.asarray(b, float)).max() <= X_TOL
+    e = pkg.calculate_reprojection_errors(obs, Xr, poses, session=s)
+    assert np.allclose(e, port.reprojection_errors(obs, Xr, poses), rtol=ERR_RTOL)
+    assert pkg.triangulate_point([[10, 10], [None, None], [None, None]], poses, session=s) == [None, None, None]
+    assert pkg.calculate_reprojection_error([[10, 10], [None, None], [None, None]], [0, 0, 1.0], poses, session=s) is None
+    frames, _, poses4, K4 = synth.make_frame_pool(4, 3, 2, seed=8)
+    s4 = pkg.MocapSession([K4] * 4)
+    port4 = RefPort([K4] * 4)
+    for b in range(2):
+        pts = []
+        for c in range(4):
+            img, p = pkg.find_dot(as3(frames[b, c]), session=s4)
+            assert p == port4.find_dot(as3(frames[b, c]))
+            pts.append(p)
+        assert pkg.find_dot(np.zeros((480, 640, 3), np.uint8), session=s4)[1] == [[None, None]]
+        e, o, _ = pkg.find_point_correspondance_and_object_points([list(map(list, p)) for p in pts], poses4, [None] * 4, session=s4)
+        e2, o2, _ = port4.match_and_triangulate(pts, poses4)
+        assert len(e) == len(e2)
+        assert np.abs(o - np.asarray(o2, dtype=np.float64)).max() <= X_TOL
+        assert np.allclose(e, e2, rtol=ERR_RTOL)
+
+
+def test_world_transform_epilogue(torch):
+    z = load_golden("pipe_c4_m4")
+    C = 4; B = z["blob_n"].shape[0]
+    ctx = _ctx(C, max_blobs=64, max_roots=128)
+    ctx.set_cameras([z["K"]] * C, poses_from(z))
+    M = np.array([[0.9, 0.1, 0, 0.3], [-0.1, 0.9, 0.05, -0.2], [0, -0.05, 1.1, 0.7], [0, 0, 0, 1.0]])
+    ctx.set_world_transform(M)
+    xy = torch.from_numpy(z["blob_xy"].reshape(B * C, 64, 2)).cuda()
+    n = torch.from_numpy(z["blob_n"].reshape(B * C)).cuda()
+    d = ctx.match_triangulate(xy, n)
+    obj = d["obj"].cpu().numpy()
+    for b in range(B):
+        for r in range(int(z["nroot"][b])):
+            p = np.array([[-1, 0, 0], [0, -1, 0], [0, 0, 1]]) @ z["obj"][b, r]      # helpers.py:96-103
+            p = M @ np.concatenate((p, [1]))
+            p = p[:3] / p[3]
+            p[1], p[2] = p[2], p[1]
+            assert np.abs(obj[b, r] - p).max() < 1e-9
+
+
+# ------------------------------------------------------------------- BASELINE-size properties
+def test_config2_size_properties(torch):
+    """BASELINE config 2 size (4 cameras, 4 markers, 10 000 frame-sets): (i) every replica of a
+    frame-set gives bit-identical tracks wherever it sits in the batch, (ii) a permuted batch
+    gives the permuted result, (iii) recovered points sit on the ground truth to pixel-quantisation
+    accuracy, (iv) the first frame-sets equal the oracle."""
+    from oracle.ref_port import RefPort
+    C, M, P, B = 4, 4, 50, 10000
+    frames, truth, poses, K = synth.make_frame_pool(C, M, P, seed=123)
+    ctx = _ctx(C, max_roots=16)
+    ctx.set_cameras([K] * C, poses)
+    pool = torch.from_numpy(frames).cuda()
+    idx = torch.arange(B, device="cuda") % P
+    big = pool[idx].contiguous()                                # 12.3 GB resident, >> L2
+    out = ctx.pipeline(big)
+    torch.cuda.synchronize()
+    n = out["n"].cpu().numpy(); obj = out["obj"].cpu().numpy(); err = out["err"].cpu().numpy()
+    assert (out["flags"].cpu().numpy() == 0).all()
+    for p in range(P):                                          # (i)
+        sel = np.arange(p, B, P)
+        assert (n[sel] == n[p]).all()
+        assert (obj[sel, :n[p]] == obj[p, :n[p]]).all() and (err[sel, :n[p]] == err[p, :n[p]]).all()
+    perm = torch.randperm(B, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    out2 = ctx.pipeline(big[perm].contiguous())                 # (ii)
+    torch.cuda.synchronize()
+    assert torch.equal(out2["n"], out["n"][perm])
+    pn = n[perm.cpu().numpy()]
+    o2 = out2["obj"].cpu().numpy(); o1 = obj[perm.cpu().numpy()]
+    mask = np.arange(obj.shape[1])[None, :] < pn[:, None]
+    assert (o2[mask] == o1[mask]).all()
+    for p in range(P):                                          # (iii)
+        assert n[p] >= M
+        for m in range(M):
+            dmin = np.linalg.norm(obj[p, :n[p]] - truth[p, m], axis=1).min()
+            assert dmin < 0.02, (p, m, dmin)
+    port = RefPort([K] * C)                                     # (iv)
+    for b in range(3):
+        pts = [port.find_dot(as3(frames[b, c])) for c in range(C)]
+        e, o, _ = port.match_and_triangulate(pts, poses)
+        assert len(e) == n[b]
+        assert np.abs(obj[b, :n[b]] - np.asarray(o, dtype=np.float64)).max() <= X_TOL
