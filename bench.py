@@ -109,8 +109,11 @@ def _cpu_init(K, poses):
     _W["poses"] = poses
 
 
-def _cpu_one(frame_set):
-    port, poses = _W["port"], _W["poses"]
+def _cpu_one(index):
+    # frames are inherited through fork (_W["frames"] is set before the pool starts): tasks carry
+    # an index only, so no image bytes travel through pipes
+    port, poses, frames = _W["port"], _W["poses"], _W["frames"]
+    frame_set = frames[index % len(frames)]
     pts = [port.find_dot(np.repeat(img[:, :, None], 3, axis=2)) for img in frame_set]
     e, o, _ = port.match_and_triangulate(pts, poses)
     return len(e)
@@ -118,7 +121,7 @@ def _cpu_one(frame_set):
 
 def cpu_pass(pool_obj, frames, n_sets):
     t0 = time.perf_counter()
-    got = pool_obj.map(_cpu_one, [frames[i % len(frames)] for i in range(n_sets)], chunksize=max(1, n_sets // (8 * pool_obj._processes)))
+    got = pool_obj.map(_cpu_one, range(n_sets), chunksize=max(1, n_sets // (8 * pool_obj._processes)))
     return time.perf_counter() - t0, sum(got)
 
 
@@ -128,7 +131,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     frames, truth, poses, K = make_pool()
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    _W["frames"] = frames
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_cpu_init, initargs=(K, poses)) as pool_obj:
         # size one step to ~4 s of wall time on this box
@@ -233,6 +237,13 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     value = BATCH * world * args.steps / (ms_total * 1e-3)
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "ms_per_step": ms_total / args.steps, "kernel_ms": kern_ms}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- e2e: host buffers through the C-ABI host entry point --------------------------------
     host_frames = torch.empty(batch.shape, dtype=torch.uint8).pin_memory()
     host_frames.copy_(batch)
@@ -256,11 +267,14 @@ def run_gpu_arm(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        alg_bytes = bytes_per_step                               # C*W*H bytes per frame-set, read once
+        # algorithmic bytes: C*W*H bytes per frame-set, read exactly once; a step is split into
+        # kern_n / steps launches (4096 frame-sets each), so per launch: step bytes * steps / launches
+        alg_bytes = bytes_per_step * args.steps / kern_n if kern_n else None
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
         # ---- CPU baseline: the oracle port on this box, bounded sample ---------------------
         import multiprocessing as mp
-        cores = os.cpu_count() or 1
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        _W["frames"] = frames
         mctx = mp.get_context("fork")
         with mctx.Pool(cores, initializer=_cpu_init, initargs=(K, poses)) as pool_obj:
             cpu_pass(pool_obj, frames, cores * 2)                  # spin the workers up
@@ -283,7 +297,7 @@ def run_gpu_arm(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_threshold_segments_c1", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes // max(1, kern_n // args.steps)) if kern_n else None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes) if alg_bytes else None,
                          "avg_launch_ms": kern_ms, "launches_timed": kern_n,
                          "whole_step_frac": (bytes_per_step * args.steps / (ms_total * 1e-3) / 1e9) / peak},
             "cpu_baseline": {"value": sample / t_cpu, "unit": "frame-sets/s", "cores": cores, "kind": "port",
@@ -302,6 +316,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--profile", action="store_true",
+                    help="resident steps only (no e2e, no CPU baseline): for runs under ncu; prints no bench line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
