@@ -161,17 +161,30 @@ typedef struct mocap_ba_options {
     double xtol;        /* 1e-8  (scipy default)                 */
     double gtol;        /* 1e-8  (scipy default)                 */
     int    max_nfev;    /* 0 -> 100 * n_params (scipy default)   */
-    int    jacobian;    /* 0: 2-point finite differences (scipy default, what the reference runs) */
+    int    jacobian;    /* 0: 2-point finite differences of the float32 residuals -- exactly what scipy
+                              differentiates for the reference (percent-level quantisation noise,
+                              SURVEY.md section 7); 1 (default): the same differences taken before the
+                              float32 cast */
+    int    prefit;      /* 1 (default): first run a classic Levenberg-Marquardt bundle adjustment over
+                              poses AND points (analytic Jacobians, per-point 3x3 blocks eliminated by
+                              Schur complement, dense reduced camera system) on the plain squared
+                              reprojection error, then polish on the reference objective; 0: reference
+                              iteration only */
+    int    prefit_max_iter;  /* 50 */
 } mocap_ba_options;
 
 typedef struct mocap_ba_report {
-    double cost_initial;   /* 0.5 * sum log1p(r^2) at the start                 */
-    double cost_final;
-    double optimality;     /* ||J^T f||_inf at the end                           */
-    int    n_iterations;
-    int    n_fev;          /* residual-vector evaluations (each = n_points DLTs) */
-    int    status;         /* scipy-style: 0 max_nfev, 1 gtol, 2 ftol, 3 xtol, 4 both */
+    double cost_initial;   /* reference objective 0.5 * sum log1p(r^2) at the start   */
+    double cost_final;     /* ... at the returned poses                                */
+    double optimality;     /* ||J^T f||_inf at the end                                 */
+    int    n_iterations;   /* trust-region iterations on the reference objective       */
+    int    n_fev;          /* residual-vector evaluations (each = n_points DLTs)       */
+    int    status;         /* scipy-style: 0 max_nfev, 1 gtol, 2 ftol, 3 xtol, 4 both  */
     int    n_residuals;
+    double prefit_cost_initial;  /* 0.5 * sum of squared pixel residuals before / after the prefit */
+    double prefit_cost_final;
+    int    prefit_iterations;
+    int    n_launches;     /* kernels launched by this call                            */
 } mocap_ba_report;
 
 MOCAP_API void mocap_ba_default_options(mocap_ba_options* opt);

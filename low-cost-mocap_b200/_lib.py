@@ -26,12 +26,14 @@ class Config(C.Structure):
 
 class BAOptions(C.Structure):
     _fields_ = [("ftol", C.c_double), ("xtol", C.c_double), ("gtol", C.c_double),
-                ("max_nfev", C.c_int), ("jacobian", C.c_int)]
+                ("max_nfev", C.c_int), ("jacobian", C.c_int), ("prefit", C.c_int), ("prefit_max_iter", C.c_int)]
 
 
 class BAReport(C.Structure):
     _fields_ = [("cost_initial", C.c_double), ("cost_final", C.c_double), ("optimality", C.c_double),
-                ("n_iterations", C.c_int), ("n_fev", C.c_int), ("status", C.c_int), ("n_residuals", C.c_int)]
+                ("n_iterations", C.c_int), ("n_fev", C.c_int), ("status", C.c_int), ("n_residuals", C.c_int),
+                ("prefit_cost_initial", C.c_double), ("prefit_cost_final", C.c_double),
+                ("prefit_iterations", C.c_int), ("n_launches", C.c_int)]
 
 
 # every symbol include/mocap_b200.h declares: name -> (restype, argtypes)

@@ -164,6 +164,7 @@ int mocap_set_cameras(mocap_ctx* ctx, const double* K, const double* R, const do
     for (int c = 0; c < C; ++c) {
         memcpy(T.R[c], R + 9 * c, 9 * sizeof(double));
         memcpy(T.t[c], t + 3 * c, 3 * sizeof(double));
+        memcpy(T.Kmat[c], K + 9 * c, 9 * sizeof(double));
         T.fx[c] = K[9 * c + 0]; T.fy[c] = K[9 * c + 4]; T.cx[c] = K[9 * c + 2]; T.cy[c] = K[9 * c + 5];
     }
     for (int k = 0; k < C; ++k)

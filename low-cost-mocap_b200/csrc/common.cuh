@@ -20,6 +20,7 @@ struct CameraTables {
     double R[MOCAP_MAX_CAM][9];
     double t[MOCAP_MAX_CAM][3];
     double fx[MOCAP_MAX_CAM], fy[MOCAP_MAX_CAM], cx[MOCAP_MAX_CAM], cy[MOCAP_MAX_CAM];  // cv.projectPoints reads these four of K
+    double Kmat[MOCAP_MAX_CAM][9];                 // full intrinsics (S4 rebuilds K_k [R|t] for trial poses)
     double world[16];                              // to_world_coords_matrix (helpers.py:99)
     int    use_world;
     int    n_cam;
