@@ -108,7 +108,7 @@ void mocap_destroy(mocap_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaDeviceSynchronize();
     cudaFree(ctx->d_tables);
-    cudaFree(ctx->d_seg_count); cudaFree(ctx->d_seg_list);
+    cudaFree(ctx->d_seg_count); cudaFree(ctx->d_seg_list); cudaFree(ctx->d_worklist); cudaFree(ctx->d_work_count);
     cudaFree(ctx->d_blob_xy); cudaFree(ctx->d_blob_n); cudaFree(ctx->d_img_flags);
     cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
     cudaFree(ctx->d_obj); cudaFree(ctx->d_err); cudaFree(ctx->d_nobj); cudaFree(ctx->d_setflags);
@@ -201,12 +201,15 @@ int mocap_set_world_transform(mocap_ctx* ctx, const double* M) {
 static int ensure_images(mocap_ctx* ctx, int n_images) {
     if (n_images <= ctx->cap_images) return MOCAP_OK;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->d_seg_count); cudaFree(ctx->d_seg_list); cudaFree(ctx->d_blob_xy); cudaFree(ctx->d_blob_n); cudaFree(ctx->d_img_flags);
-    ctx->d_seg_count = nullptr; ctx->d_seg_list = nullptr; ctx->d_blob_xy = nullptr; ctx->d_blob_n = nullptr; ctx->d_img_flags = nullptr;
+    cudaFree(ctx->d_seg_count); cudaFree(ctx->d_seg_list); cudaFree(ctx->d_worklist); cudaFree(ctx->d_work_count); cudaFree(ctx->d_blob_xy); cudaFree(ctx->d_blob_n); cudaFree(ctx->d_img_flags);
+    ctx->d_seg_count = nullptr; ctx->d_seg_list = nullptr; ctx->d_worklist = nullptr; ctx->d_work_count = nullptr; ctx->d_blob_xy = nullptr; ctx->d_blob_n = nullptr; ctx->d_img_flags = nullptr;
     ctx->cap_images = 0;
     const size_t n = (size_t)n_images;
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_seg_count, n * sizeof(uint32_t)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_seg_list, n * ctx->cfg.max_segments * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_worklist, n * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_work_count, 2 * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_work_count, 0, 2 * sizeof(uint32_t), ctx->stream));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_blob_xy, n * ctx->cfg.max_blobs * 2 * sizeof(int32_t)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_blob_n, n * sizeof(int32_t)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_img_flags, n * sizeof(int32_t)));

@@ -122,6 +122,13 @@ k_threshold_segments_c3(const uint4* __restrict__ frames, long long n_seg, int s
 // ---------------------------------------------------------------------------------------------
 // sparse per-image reduction
 // ---------------------------------------------------------------------------------------------
+// NT == 32: the group is one warp (several images per CTA, warp-level synchronisation only);
+// NT  > 32: the group is the whole CTA.
+template <int NT>
+__device__ __forceinline__ void gsync() {
+    if (NT == 32) __syncwarp(); else __syncthreads();
+}
+
 template <int NT>
 __device__ __forceinline__ unsigned block_scan_excl(unsigned v, unsigned& total, unsigned* wsum) {
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -130,6 +137,10 @@ __device__ __forceinline__ unsigned block_scan_excl(unsigned v, unsigned& total,
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= (unsigned)o) x += y;
+    }
+    if (NT == 32) {
+        total = __shfl_sync(0xffffffffu, x, 31);
+        return x - v;
     }
     if (lane == 31) wsum[wid] = x;
     __syncthreads();
@@ -205,11 +216,13 @@ __device__ __forceinline__ BlobSmem carve_blob_smem(unsigned char* raw, int E) {
 }
 
 // Block-wide: the n segments in sm.seg[0..n) (unsorted) -> blobs of one image.
-template <int NT>
-__device__ void blob_reduce(BlobSmem sm, int n, int E, int W, int H, int max_blobs,
+// Returns false (group-uniform) without writing anything when STRICT and a capacity (runs > E,
+// blobs > ACC) is exceeded: the caller then hands the image to the full-size kernel.
+template <int NT, bool STRICT>
+__device__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int W, int H, int max_blobs,
                             int32_t* __restrict__ out_xy, int32_t* __restrict__ out_n,
                             int64_t* __restrict__ out_mom, int32_t* __restrict__ out_flags, int flags_in) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x % NT;
     const int SPR = W / MOCAP_SEG_PX;     // segments per row
     int flags = flags_in;
 
@@ -217,7 +230,7 @@ __device__ void blob_reduce(BlobSmem sm, int n, int E, int W, int H, int max_blo
     int n2 = 1;
     while (n2 < n) n2 <<= 1;
     for (int i = n + tid; i < n2; i += NT) sm.seg[i] = SEG_PAD;
-    __syncthreads();
+    gsync<NT>();
     for (int k = 2; k <= n2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tid; i < n2; i += NT) {
@@ -228,7 +241,7 @@ __device__ void blob_reduce(BlobSmem sm, int n, int E, int W, int H, int max_blo
                     if ((a > b) == up) { sm.seg[i] = b; sm.seg[ixj] = a; }
                 }
             }
-            __syncthreads();
+            gsync<NT>();
         }
     }
 
@@ -246,9 +259,10 @@ __device__ void blob_reduce(BlobSmem sm, int n, int E, int W, int H, int max_blo
         }
         n_runs = carry;
     }
-    if (n_runs > (unsigned)E) {          // cannot label: report and emit nothing (block-uniform)
+    if (n_runs > (unsigned)E) {          // cannot label: report and emit nothing (group-uniform)
+        if (STRICT) return false;
         if (tid == 0) { *out_n = 0; if (out_flags) *out_flags = flags | MOCAP_F_SEGMENTS; }
-        return;
+        return true;
     }
     for (int i = tid; i < n; i += NT) {
         unsigned s = sm.seg[i] & 0xffffu;
@@ -263,7 +277,7 @@ __device__ void blob_reduce(BlobSmem sm, int n, int E, int W, int H, int max_blo
             ++id;
         }
     }
-    __syncthreads();
+    gsync<NT>();
 
     // ---- 3. 8-connectivity unions: right neighbour across the segment boundary, and the row above
     for (unsigned id = tid; id < n_runs; id += NT) {
@@ -299,13 +313,13 @@ __device__ void blob_reduce(BlobSmem sm, int n, int E, int W, int H, int max_blo
             }
         }
     }
-    __syncthreads();
+    gsync<NT>();
     // flatten (two phases so that nobody chases a pointer that is being rewritten;
     // sm.rank is free until step 4 and run ids fit 16 bits because n_runs <= E <= 4096)
     for (unsigned id = tid; id < n_runs; id += NT) sm.rank[id] = (uint16_t)uf_find(sm.parent, id);
-    __syncthreads();
+    gsync<NT>();
     for (unsigned id = tid; id < n_runs; id += NT) sm.parent[id] = sm.rank[id];
-    __syncthreads();
+    gsync<NT>();
 
     // ---- 4. rank the roots (ascending run id == ascending raster position of the blob's first pixel)
     unsigned n_blobs = 0;
@@ -321,16 +335,19 @@ __device__ void blob_reduce(BlobSmem sm, int n, int E, int W, int H, int max_blo
         }
         n_blobs = carry;
     }
-    if (n_blobs > MOCAP_ACC_CAP) flags |= MOCAP_F_BLOBS;
-    const unsigned nb = min(n_blobs, (unsigned)MOCAP_ACC_CAP);
+    if (n_blobs > (unsigned)ACC) {
+        if (STRICT) return false;
+        flags |= MOCAP_F_BLOBS;
+    }
+    const unsigned nb = min(n_blobs, (unsigned)ACC);
     for (unsigned k = tid; k < nb * 4; k += NT) sm.acc[k] = 0ull;
-    __syncthreads();
+    gsync<NT>();
 
     // ---- 5. per-run share of the 2x2-cell moments.  A cell is owned by the run holding its
     //         top-left corner, or its top-right corner when the top-left pixel is clear.
     for (unsigned id = tid; id < n_runs; id += NT) {
         const unsigned blob = sm.rank[sm.parent[id]];
-        if (blob >= (unsigned)MOCAP_ACC_CAP) continue;
+        if (blob >= (unsigned)ACC) continue;
         const int i = sm.node_seg[id];
         const unsigned rb = sm.node_bits[id];
         const uint32_t e = sm.seg[i];
@@ -372,7 +389,7 @@ __device__ void blob_reduce(BlobSmem sm, int n, int E, int W, int H, int max_blo
         }
         atomicAdd(a + 3, (unsigned long long)__popc(rb));
     }
-    __syncthreads();
+    gsync<NT>();
 
     // ---- 6. keep blobs with non-zero polygon area (helpers.py:153), emit in reverse raster order
     unsigned n_keep = 0;
@@ -415,33 +432,89 @@ __device__ void blob_reduce(BlobSmem sm, int n, int E, int W, int H, int max_blo
         *out_n = (int)min(n_keep, (unsigned)max_blobs);
         if (out_flags) *out_flags = flags;
     }
+    return true;
 }
 
+// Sparse reduction, common case: one WARP per image (warp-level synchronisation only).  Images
+// with more than WE segments / runs or more than WACC blobs are appended to a worklist for the
+// full-size kernel below.  Shared memory per warp is a fixed small slab.
+#define BLOB_WE   128     // segments (and runs) a warp handles
+#define BLOB_WACC 64      // blobs a warp accumulates
+struct WarpSlab {
+    unsigned long long acc[BLOB_WACC * 4];
+    uint32_t seg[BLOB_WE];
+    unsigned parent[BLOB_WE];
+    uint16_t base[BLOB_WE], node_seg[BLOB_WE], node_bits[BLOB_WE], rank[BLOB_WE];
+};
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32)
+k_blob_reduce_warp(uint32_t* __restrict__ seg_count, const uint32_t* __restrict__ seg_list, int n_images, int E,
+                   int W, int H, int max_blobs, int32_t* __restrict__ blob_xy, int32_t* __restrict__ blob_n,
+                   int64_t* __restrict__ blob_mom, int32_t* __restrict__ img_flags,
+                   uint32_t* __restrict__ worklist, uint32_t* __restrict__ work_count) {
+    __shared__ WarpSlab slabs[WPB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int img = blockIdx.x * WPB + warp;
+    if (img >= n_images) return;
+    const unsigned cnt = seg_count[img];
+    int32_t* ofl = img_flags ? img_flags + img : nullptr;
+    if (cnt == 0) {
+        if (lane == 0) { blob_n[img] = 0; if (ofl) *ofl = 0; }
+        return;
+    }
+    bool ok = cnt <= BLOB_WE;
+    if (ok) {
+        WarpSlab& sl = slabs[warp];
+        BlobSmem sm;
+        sm.seg = sl.seg; sm.parent = sl.parent; sm.base = sl.base; sm.node_seg = sl.node_seg;
+        sm.node_bits = sl.node_bits; sm.rank = sl.rank; sm.acc = sl.acc; sm.wsum = nullptr;
+        const uint32_t* src = seg_list + (size_t)img * E;
+        for (int i = lane; i < (int)cnt; i += 32) sm.seg[i] = src[i];
+        __syncwarp();
+        ok = blob_reduce<32, true>(sm, (int)cnt, BLOB_WE, BLOB_WACC, W, H, max_blobs, blob_xy + (size_t)img * max_blobs * 2,
+                                   blob_n + img, blob_mom ? blob_mom + (size_t)img * max_blobs * 4 : nullptr, ofl, 0);
+    }
+    if (lane == 0) {
+        if (ok) seg_count[img] = 0;                             // self-cleaning: ready for the next batch
+        else worklist[atomicAdd(work_count, 1u)] = (uint32_t)img;
+    }
+}
+
+// Full-size reduction for the images the warp kernel deferred: persistent CTAs walk the worklist.
 template <int NT>
 __global__ void __launch_bounds__(NT)
 k_blob_reduce(uint32_t* __restrict__ seg_count, const uint32_t* __restrict__ seg_list, int E, int W, int H,
               int max_blobs, int32_t* __restrict__ blob_xy, int32_t* __restrict__ blob_n,
-              int64_t* __restrict__ blob_mom, int32_t* __restrict__ img_flags) {
+              int64_t* __restrict__ blob_mom, int32_t* __restrict__ img_flags,
+              const uint32_t* __restrict__ worklist, uint32_t* __restrict__ work_count, uint32_t* __restrict__ done_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BlobSmem sm = carve_blob_smem(smem_raw, E);
-    const int img = blockIdx.x;
-    const unsigned cnt = seg_count[img];
-    __syncthreads();
-    if (threadIdx.x == 0) seg_count[img] = 0;          // self-cleaning: ready for the next batch
-    int flags = 0;
-    int n = (int)cnt;
-    if (cnt > (unsigned)E) { flags |= MOCAP_F_SEGMENTS; n = 0; }
-    int32_t* oxy = blob_xy + (size_t)img * max_blobs * 2;
-    int64_t* omom = blob_mom ? blob_mom + (size_t)img * max_blobs * 4 : nullptr;
-    int32_t* ofl = img_flags ? img_flags + img : nullptr;
-    if (n == 0) {
-        if (threadIdx.x == 0) { blob_n[img] = 0; if (ofl) *ofl = flags; }
-        return;
+    const unsigned n_work = *work_count;
+    for (unsigned w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int img = (int)worklist[w];
+        const unsigned cnt = seg_count[img];
+        __syncthreads();
+        if (threadIdx.x == 0) seg_count[img] = 0;
+        int flags = 0;
+        int n = (int)cnt;
+        if (cnt > (unsigned)E) { flags |= MOCAP_F_SEGMENTS; n = 0; }
+        int32_t* ofl = img_flags ? img_flags + img : nullptr;
+        if (n == 0) {
+            if (threadIdx.x == 0) { blob_n[img] = 0; if (ofl) *ofl = flags; }
+            continue;
+        }
+        const uint32_t* src = seg_list + (size_t)img * E;
+        for (int i = threadIdx.x; i < n; i += NT) sm.seg[i] = src[i];
+        __syncthreads();
+        blob_reduce<NT, false>(sm, n, E, MOCAP_ACC_CAP, W, H, max_blobs, blob_xy + (size_t)img * max_blobs * 2, blob_n + img,
+                               blob_mom ? blob_mom + (size_t)img * max_blobs * 4 : nullptr, ofl, flags);
+        __syncthreads();
     }
-    const uint32_t* src = seg_list + (size_t)img * E;
-    for (int i = threadIdx.x; i < n; i += NT) sm.seg[i] = src[i];
-    __syncthreads();
-    blob_reduce<NT>(sm, n, E, W, H, max_blobs, oxy, blob_n + img, omom, ofl, flags);
+    if (threadIdx.x == 0) {                                     // the last CTA to finish re-arms the worklist
+        __threadfence();
+        if (atomicAdd(done_count, 1u) == gridDim.x - 1) { *work_count = 0; *done_count = 0; }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -487,11 +560,19 @@ int launch_detect(mocap_ctx* ctx, const uint8_t* frames, int n_images, int chann
         CUDA_TRY(ctx, cudaEventRecord(ctx->tim_ev[2 * ctx->tim_used + 1], ctx->stream));
         ctx->tim_used += 1;
     }
+    constexpr int WPB = 8;
+    k_blob_reduce_warp<WPB><<<(n_images + WPB - 1) / WPB, WPB * 32, 0, ctx->stream>>>(
+        ctx->d_seg_count, ctx->d_seg_list, n_images, E, c.width, c.height, c.max_blobs, blob_xy, blob_n, blob_mom, img_flags,
+        ctx->d_worklist, ctx->d_work_count);
+    CUDA_TRY(ctx, cudaGetLastError());
     constexpr int NT = 128;
     const size_t smem = blob_reduce_smem_bytes(E);
-    k_blob_reduce<NT><<<n_images, NT, smem, ctx->stream>>>(ctx->d_seg_count, ctx->d_seg_list, E, c.width, c.height,
-                                                          c.max_blobs, blob_xy, blob_n, blob_mom, img_flags);
+    const int grid2 = n_images < ctx->num_sms ? n_images : ctx->num_sms;
+    k_blob_reduce<NT><<<grid2, NT, smem, ctx->stream>>>(ctx->d_seg_count, ctx->d_seg_list, E, c.width, c.height,
+                                                       c.max_blobs, blob_xy, blob_n, blob_mom, img_flags,
+                                                       ctx->d_worklist, ctx->d_work_count, ctx->d_work_count + 1);
     CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 1;
     ctx->launches += 2;
     return MOCAP_OK;
 }

@@ -38,6 +38,8 @@ struct mocap_ctx {
     int       cap_images;
     uint32_t* d_seg_count;
     uint32_t* d_seg_list;
+    uint32_t* d_worklist;     // images deferred by the warp-level blob kernel
+    uint32_t* d_work_count;   // [2]: count, finished-CTA counter
     int32_t*  d_blob_xy;
     int32_t*  d_blob_n;
     int32_t*  d_img_flags;

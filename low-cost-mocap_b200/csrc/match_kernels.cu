@@ -27,10 +27,12 @@ struct WarpState {
     uint32_t* gprefix; // [RMAX+1]
     unsigned long long* best_key;  // [RMAX]
     uint32_t* best_g;  // [RMAX]
+    double* best_xe;   // [RMAX][4]  X and error of the best group so far
 };
 
 static __host__ __device__ size_t warp_state_bytes(int RMAX, int C, int KC) {
     size_t b = 0;
+    b += (size_t)RMAX * 32;                      // best_xe
     b += (size_t)RMAX * 8;                       // best_key
     b += (size_t)RMAX * 4 * 2 + (RMAX + 1) * 4;  // gcount, best_g, gprefix
     b += (size_t)RMAX * 2;                       // rcam, rpt
@@ -43,6 +45,7 @@ size_t match_smem_bytes(const mocap_config& cfg, int warps) {
 }
 __device__ __forceinline__ WarpState carve_warp_state(unsigned char* raw, int RMAX, int C, int KC) {
     WarpState s;
+    s.best_xe = reinterpret_cast<double*>(raw);              raw += (size_t)RMAX * 32;
     s.best_key = reinterpret_cast<unsigned long long*>(raw); raw += (size_t)RMAX * 8;
     s.gcount = reinterpret_cast<uint32_t*>(raw);             raw += (size_t)RMAX * 4;
     s.best_g = reinterpret_cast<uint32_t*>(raw);             raw += (size_t)RMAX * 4;
@@ -60,17 +63,13 @@ __device__ __forceinline__ unsigned long long err_key(double e) {
     return (unsigned long long)__double_as_longlong(e) + 1ull;    // e >= 0
 }
 
-// DLT + reprojection error of group g of root r.  Returns false when the root has < 2 views.
-__device__ __forceinline__ void eval_group(const CameraTables* __restrict__ tb, const WarpState& ws,
-                                           const int32_t* __restrict__ xy, int MB, int C, int KC,
-                                           int r, uint32_t g, double X[3], double& err, int32_t* chosen_out) {
+// views of group g of root r: the root's own blob plus, per later camera with candidates, the
+// candidate selected by g's mixed-radix digit (earliest camera = least significant digit)
+__device__ __forceinline__ int decode_group(const WarpState& ws, int C, int KC, int r, uint32_t g,
+                                            int cams[MOCAP_MAX_CAM], int pts[MOCAP_MAX_CAM]) {
     const int rc = ws.rcam[r];
-    Sym4 B;
-    sym4_zero(B);
-    int cams[MOCAP_MAX_CAM];
-    int pts[MOCAP_MAX_CAM];
-    int nv = 0;
-    cams[0] = rc; pts[0] = ws.rpt[r]; nv = 1;
+    cams[0] = rc; pts[0] = ws.rpt[r];
+    int nv = 1;
     uint32_t rem = g;
     for (int i = rc + 1; i < C; ++i) {
         const int k = ws.ncand[r * C + i];
@@ -82,6 +81,18 @@ __device__ __forceinline__ void eval_group(const CameraTables* __restrict__ tb, 
             ++nv;
         }
     }
+    return nv;
+}
+
+// DLT + reprojection error of group g of root r.
+__device__ __forceinline__ void eval_group(const CameraTables* __restrict__ tb, const WarpState& ws,
+                                           const int32_t* __restrict__ xy, int MB, int C, int KC,
+                                           int r, uint32_t g, double X[3], double& err) {
+    Sym4 B;
+    sym4_zero(B);
+    int cams[MOCAP_MAX_CAM];
+    int pts[MOCAP_MAX_CAM];
+    const int nv = decode_group(ws, C, KC, r, g, cams, pts);
     for (int k = 0; k < nv; ++k) {
         const int c = cams[k];
         const double px = (double)xy[((size_t)c * MB + pts[k]) * 2 + 0];
@@ -102,10 +113,6 @@ __device__ __forceinline__ void eval_group(const CameraTables* __restrict__ tb, 
     // a group without None entries is an int64 array in the reference (pairwise float64 sum);
     // any None turns it into an object array (left fold)
     err = mean_like_numpy(sq, 2 * nv, nv == C);
-    if (chosen_out) {
-        for (int i = 0; i < C; ++i) chosen_out[i] = -1;
-        for (int k = 0; k < nv; ++k) chosen_out[cams[k]] = pts[k];
-    }
 }
 
 __global__ void __launch_bounds__(128)
@@ -221,32 +228,39 @@ k_match_triangulate(const CameraTables* __restrict__ tb, const int32_t* __restri
     __syncwarp();
     const uint32_t total = ws.gprefix[nr];
 
-    // pass 1: every group's error; segmented warp argmin, heads fold into shared memory
+    // pass 1: every group's point and error; segmented warp argmin; the head lane of every root's
+    // segment pulls the winner's point over by shuffle and folds it into shared memory
     for (uint32_t w0 = 0; w0 < total; w0 += 32) {
         const uint32_t w = w0 + lane;
         int r = -1;
         uint32_t g = 0;
         unsigned long long key = ~0ull;
+        double X[3] = {0.0, 0.0, 0.0}, e = 0.0;
         if (w < total) {
             int lo = 0, hi = nr;                               // last r with gprefix[r] <= w
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ws.gprefix[mid] <= w) lo = mid; else hi = mid; }
             r = lo;
-            while (ws.gcount[r] == 0) ++r;                     // skip empty roots sharing the same prefix
             g = w - ws.gprefix[r];
-            double X[3], e;
-            eval_group(tb, ws, xy, MB, C, KC, r, g, X, e, nullptr);
+            eval_group(tb, ws, xy, MB, C, KC, r, g, X, e);
             key = err_key(e);
         }
+        int src = lane;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int r2 = __shfl_down_sync(FULL_MASK, r, o);
             const uint32_t g2 = __shfl_down_sync(FULL_MASK, g, o);
             const unsigned long long k2 = __shfl_down_sync(FULL_MASK, key, o);
-            if (lane + o < 32 && r2 == r && (k2 < key || (k2 == key && g2 < g))) { key = k2; g = g2; }
+            const int s2 = __shfl_down_sync(FULL_MASK, src, o);
+            if (lane + o < 32 && r2 == r && (k2 < key || (k2 == key && g2 < g))) { key = k2; g = g2; src = s2; }
         }
+        const double bx = __shfl_sync(FULL_MASK, X[0], src), by = __shfl_sync(FULL_MASK, X[1], src);
+        const double bz = __shfl_sync(FULL_MASK, X[2], src), be = __shfl_sync(FULL_MASK, e, src);
         const int rprev = __shfl_up_sync(FULL_MASK, r, 1);
         const bool head = (r >= 0) && (lane == 0 || rprev != r);
-        if (head && key < ws.best_key[r]) { ws.best_key[r] = key; ws.best_g[r] = g; }   // ties keep the earlier group (np.argmin)
+        if (head && key < ws.best_key[r]) {                    // ties keep the earlier group (np.argmin)
+            ws.best_key[r] = key; ws.best_g[r] = g;
+            ws.best_xe[4 * r + 0] = bx; ws.best_xe[4 * r + 1] = by; ws.best_xe[4 * r + 2] = bz; ws.best_xe[4 * r + 3] = be;
+        }
         __syncwarp();
     }
 
@@ -261,8 +275,14 @@ k_match_triangulate(const CameraTables* __restrict__ tb, const int32_t* __restri
         const unsigned bal = __ballot_sync(FULL_MASK, has);
         if (has) {
             const int o = n_out + __popc(bal & ((1u << lane) - 1u));
-            double X[3], e;
-            eval_group(tb, ws, xy, MB, C, KC, r, ws.best_g[r], X, e, ch_s ? ch_s + (size_t)o * C : nullptr);
+            double X[3] = {ws.best_xe[4 * r], ws.best_xe[4 * r + 1], ws.best_xe[4 * r + 2]};
+            const double e = ws.best_xe[4 * r + 3];
+            if (ch_s) {
+                int cams[MOCAP_MAX_CAM], pts[MOCAP_MAX_CAM];
+                const int nv = decode_group(ws, C, KC, r, ws.best_g[r], cams, pts);
+                for (int i = 0; i < C; ++i) ch_s[(size_t)o * C + i] = -1;
+                for (int k = 0; k < nv; ++k) ch_s[(size_t)o * C + cams[k]] = pts[k];
+            }
             if (tb->use_world) {                               // helpers.py:96-103
                 const double* M = tb->world;
                 const double x = -X[0], y = -X[1], z = X[2];
