@@ -104,6 +104,11 @@ _W = {}
 def _cpu_init(K, poses):
     import cv2
     cv2.setNumThreads(1)
+    try:                                   # one worker per core: keep BLAS/OpenMP pools from oversubscribing
+        from threadpoolctl import threadpool_limits
+        _W["limit"] = threadpool_limits(1)
+    except Exception:
+        pass
     from oracle.ref_port import RefPort
     _W["port"] = RefPort([K] * len(poses))
     _W["poses"] = poses
@@ -191,14 +196,15 @@ def run_gpu_arm(args):
     owned = torch.from_numpy(sharding.shard_indices(BATCH * world, rank, world)).to(dev)
     batch = pool_dev[owned % POOL].contiguous()                   # [BATCH, C, H, W] uint8, 12.3 GB
     del pool_dev
-    out = ctx.alloc_tracks(BATCH, dev)
+    # the matcher writes straight into the all-gather send buffer (one flat allocation)
+    tracks = sharding.TrackBuffer(BATCH, MAX_ROOTS, dev)
+    out = tracks.views
     bytes_per_step = batch.numel()
 
     def step():
         ctx.pipeline(batch, out=out)
         if world > 1:
-            rec = sharding.pack_tracks(out["obj"], out["err"], out["n"])
-            return sharding.all_gather_tracks(rec, BATCH * world)
+            return tracks.all_gather()       # ONE NCCL all-gather per batch; consumers read views
         return None
 
     def sync_all():
@@ -231,7 +237,7 @@ def run_gpu_arm(args):
     ms_total = float(ms.item())
     launches = ctx.launch_count() - launches0
     if world > 1:
-        launches += 5 * args.steps          # pack (3 slice copies + cast) + transpose copy of the gather, torch kernels
+        launches += args.steps              # the NCCL all-gather kernel
     kern_ms, kern_n = ctx.detect_kernel_ms(reset=True)
     ctx.enable_kernel_timing(False)
     clocks = sampler.stop() if rank == 0 else None

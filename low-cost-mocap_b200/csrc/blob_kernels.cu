@@ -183,10 +183,18 @@ __device__ __forceinline__ void uf_unite(unsigned* parent, unsigned a, unsigned 
     }
 }
 __device__ __forceinline__ unsigned run_starts(unsigned m) { return m & ~(m << 1) & 0xffffu; }
+// sum of the indices of the set bits (branch-free: weight 2^k times the bits whose index has bit k)
 __device__ __forceinline__ int bit_index_sum(unsigned m) {
-    int s = 0;
-    while (m) { s += __ffs(m) - 1; m &= m - 1; }
-    return s;
+    return __popc(m & 0xAAAAAAAAu) + 2 * __popc(m & 0xCCCCCCCCu) + 4 * __popc(m & 0xF0F0F0F0u) +
+           8 * __popc(m & 0xFF00FF00u) + 16 * __popc(m & 0xFFFF0000u);
+}
+__device__ __forceinline__ int seg_lower_bound(const uint32_t* seg, int n, uint32_t pos) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((seg[mid] >> 16) < pos) lo = mid + 1; else hi = mid;
+    }
+    return lo;
 }
 
 struct BlobSmem {
@@ -216,9 +224,14 @@ __device__ __forceinline__ BlobSmem carve_blob_smem(unsigned char* raw, int E) {
 }
 
 // Block-wide: the n segments in sm.seg[0..n) (unsorted) -> blobs of one image.
+template <bool WIDE>
+__device__ __forceinline__ unsigned long long acc_get(const unsigned long long* acc, unsigned idx) {
+    return WIDE ? acc[idx] : (unsigned long long)reinterpret_cast<const unsigned*>(acc)[idx];
+}
+
 // Returns false (group-uniform) without writing anything when STRICT and a capacity (runs > E,
 // blobs > ACC) is exceeded: the caller then hands the image to the full-size kernel.
-template <int NT, bool STRICT>
+template <int NT, bool STRICT, bool WIDE>
 __device__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int W, int H, int max_blobs,
                             int32_t* __restrict__ out_xy, int32_t* __restrict__ out_n,
                             int64_t* __restrict__ out_mom, int32_t* __restrict__ out_flags, int flags_in) {
@@ -226,22 +239,36 @@ __device__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int W, int H, in
     const int SPR = W / MOCAP_SEG_PX;     // segments per row
     int flags = flags_in;
 
-    // ---- 1. raster order: bitonic sort of (pos<<16 | mask)
-    int n2 = 1;
-    while (n2 < n) n2 <<= 1;
-    for (int i = n + tid; i < n2; i += NT) sm.seg[i] = SEG_PAD;
-    gsync<NT>();
-    for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < n2; i += NT) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const uint32_t a = sm.seg[i], b = sm.seg[ixj];
-                    const bool up = ((i & k) == 0);
-                    if ((a > b) == up) { sm.seg[i] = b; sm.seg[ixj] = a; }
+    // ---- 1. raster order of (pos<<16 | mask).  Warp groups (n <= 128): rank sort -- every element
+    //         counts the smaller ones (keys are unique), no barriers; CTA groups: bitonic sort.
+    if (NT == 32) {
+        uint32_t* tmp = reinterpret_cast<uint32_t*>(sm.parent);     // free until step 2
+        for (int i = tid; i < n; i += NT) {
+            const uint32_t e = sm.seg[i];
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += (sm.seg[j] < e) ? 1 : 0;
+            tmp[rank] = e;
+        }
+        gsync<NT>();
+        for (int i = tid; i < n; i += NT) sm.seg[i] = tmp[i];
+        gsync<NT>();
+    } else {
+        int n2 = 1;
+        while (n2 < n) n2 <<= 1;
+        for (int i = n + tid; i < n2; i += NT) sm.seg[i] = SEG_PAD;
+        gsync<NT>();
+        for (int k = 2; k <= n2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < n2; i += NT) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const uint32_t a = sm.seg[i], b = sm.seg[ixj];
+                        const bool up = ((i & k) == 0);
+                        if ((a > b) == up) { sm.seg[i] = b; sm.seg[ixj] = a; }
+                    }
                 }
+                gsync<NT>();
             }
-            gsync<NT>();
         }
     }
 
@@ -289,27 +316,28 @@ __device__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int W, int H, in
             const uint32_t e2 = sm.seg[i + 1];
             if ((e2 >> 16) == p + 1 && (e2 & 1u)) uf_unite(sm.parent, id, sm.base[i + 1]);
         }
-        if (y > 0) {
+        if (y > 0) {                                               // the <= 3 segments of row y-1 that touch this run
             const unsigned ext = (rb | (rb << 1) | (rb >> 1)) & 0xffffu;
-            int j = seg_find(sm.seg, n, p - SPR);
-            if (j >= 0) {
-                unsigned s = sm.seg[j] & 0xffffu, r = 0;
-                while (s) {
-                    const unsigned b = s & (0u - s);
-                    const unsigned run = s & ~(s + b);
-                    s &= ~run;
-                    if (run & ext) uf_unite(sm.parent, id, sm.base[j] + r);
-                    ++r;
+            const uint32_t q = p - SPR;
+            const int lo = seg_lower_bound(sm.seg, n, sc > 0 ? q - 1 : q);
+            for (int j = lo; j < n && j < lo + 3; ++j) {
+                const uint32_t ej = sm.seg[j], pj = ej >> 16;
+                if (pj > q + 1) break;
+                const unsigned mm = ej & 0xffffu;
+                if (pj == q) {
+                    unsigned sbits = mm, r = 0;
+                    while (sbits) {
+                        const unsigned b = sbits & (0u - sbits);
+                        const unsigned run = sbits & ~(sbits + b);
+                        sbits &= ~run;
+                        if (run & ext) uf_unite(sm.parent, id, sm.base[j] + r);
+                        ++r;
+                    }
+                } else if (pj + 1 == q) {                           // left neighbour segment (only searched when sc > 0)
+                    if ((rb & 1u) && (mm & 0x8000u)) uf_unite(sm.parent, id, sm.base[j] + __popc(run_starts(mm)) - 1);
+                } else if (sc + 1 < SPR) {                          // pj == q + 1: right neighbour segment
+                    if ((rb & 0x8000u) && (mm & 1u)) uf_unite(sm.parent, id, sm.base[j]);
                 }
-            }
-            if ((rb & 1u) && sc > 0) {
-                j = seg_find(sm.seg, n, p - SPR - 1);
-                if (j >= 0 && (sm.seg[j] & 0x8000u))
-                    uf_unite(sm.parent, id, sm.base[j] + __popc(run_starts(sm.seg[j] & 0xffffu)) - 1);
-            }
-            if ((rb & 0x8000u) && sc + 1 < SPR) {
-                j = seg_find(sm.seg, n, p - SPR + 1);
-                if (j >= 0 && (sm.seg[j] & 1u)) uf_unite(sm.parent, id, sm.base[j]);
             }
         }
     }
@@ -340,7 +368,7 @@ __device__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int W, int H, in
         flags |= MOCAP_F_BLOBS;
     }
     const unsigned nb = min(n_blobs, (unsigned)ACC);
-    for (unsigned k = tid; k < nb * 4; k += NT) sm.acc[k] = 0ull;
+    for (unsigned k = tid; k < nb * 4; k += NT) { if (WIDE) sm.acc[k] = 0ull; else reinterpret_cast<unsigned*>(sm.acc)[k] = 0u; }
     gsync<NT>();
 
     // ---- 5. per-run share of the 2x2-cell moments.  A cell is owned by the run holding its
@@ -360,10 +388,15 @@ __device__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int W, int H, in
         if (sc + 1 < SPR && i + 1 < n && (sm.seg[i + 1] >> 16) == p + 1) T |= (sm.seg[i + 1] & 1u) << 17;
         unsigned Bw = 0;
         if (y + 1 < H) {
-            int j = seg_find(sm.seg, n, p + SPR);
-            if (j >= 0) Bw |= (sm.seg[j] & 0xffffu) << 1;
-            if (sc > 0) { j = seg_find(sm.seg, n, p + SPR - 1); if (j >= 0) Bw |= (sm.seg[j] >> 15) & 1u; }
-            if (sc + 1 < SPR) { j = seg_find(sm.seg, n, p + SPR + 1); if (j >= 0) Bw |= (sm.seg[j] & 1u) << 17; }
+            const uint32_t q = p + SPR;
+            const int lo = seg_lower_bound(sm.seg, n, sc > 0 ? q - 1 : q);
+            for (int j = lo; j < n && j < lo + 3; ++j) {
+                const uint32_t ej = sm.seg[j], pj = ej >> 16;
+                if (pj > q + 1) break;
+                if (pj == q) Bw |= (ej & 0xffffu) << 1;
+                else if (pj + 1 == q) Bw |= (ej >> 15) & 1u;        // only searched when sc > 0
+                else if (sc + 1 < SPR) Bw |= (ej & 1u) << 17;
+            }
         }
         const unsigned Rw = rb << 1;
         const unsigned T1 = T >> 1, B1 = Bw >> 1;
@@ -381,13 +414,23 @@ __device__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int W, int H, in
         const long long a2 = 2ll * nf + ntl + ntr + nbl + nbr;
         const long long sx6 = 6 * sxf + 3ll * nf + 3 * (sx_tl + sx_tr + sx_bl + sx_br) + 2ll * (ntl + nbl) + (ntr + nbr);
         const long long sy6 = (6ll * y + 3) * nf + (3ll * y + 2) * (ntl + ntr) + (3ll * y + 1) * (nbl + nbr);
-        unsigned long long* a = sm.acc + 4 * blob;
-        if (a2) {
-            atomicAdd(a + 0, (unsigned long long)a2);
-            atomicAdd(a + 1, (unsigned long long)sx6);
-            atomicAdd(a + 2, (unsigned long long)sy6);
+        if (WIDE) {
+            unsigned long long* a = sm.acc + 4 * blob;
+            if (a2) {
+                atomicAdd(a + 0, (unsigned long long)a2);
+                atomicAdd(a + 1, (unsigned long long)sx6);
+                atomicAdd(a + 2, (unsigned long long)sy6);
+            }
+            atomicAdd(a + 3, (unsigned long long)__popc(rb));
+        } else {                                                   // 6*max(W,H)*W*H < 2^32: native 32-bit shared atomics
+            unsigned* a = reinterpret_cast<unsigned*>(sm.acc) + 4 * blob;
+            if (a2) {
+                atomicAdd(a + 0, (unsigned)a2);
+                atomicAdd(a + 1, (unsigned)sx6);
+                atomicAdd(a + 2, (unsigned)sy6);
+            }
+            atomicAdd(a + 3, (unsigned)__popc(rb));
         }
-        atomicAdd(a + 3, (unsigned long long)__popc(rb));
     }
     gsync<NT>();
 
@@ -397,7 +440,7 @@ __device__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int W, int H, in
         unsigned carry = 0;
         for (unsigned k0 = 0; k0 < nb; k0 += NT) {      // pass 1: count
             const unsigned k = k0 + tid;
-            const unsigned keep = (k < nb && sm.acc[4 * k] != 0ull) ? 1u : 0u;
+            const unsigned keep = (k < nb && acc_get<WIDE>(sm.acc, 4 * k) != 0ull) ? 1u : 0u;
             unsigned tot;
             block_scan_excl<NT>(keep, tot, sm.wsum);
             carry += tot;
@@ -406,13 +449,13 @@ __device__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int W, int H, in
         carry = 0;
         for (unsigned k0 = 0; k0 < nb; k0 += NT) {      // pass 2: place
             const unsigned k = k0 + tid;
-            const unsigned keep = (k < nb && sm.acc[4 * k] != 0ull) ? 1u : 0u;
+            const unsigned keep = (k < nb && acc_get<WIDE>(sm.acc, 4 * k) != 0ull) ? 1u : 0u;
             unsigned tot;
             const unsigned ex = block_scan_excl<NT>(keep, tot, sm.wsum);
             if (keep) {
                 const unsigned o = n_keep - 1 - (carry + ex);
                 if (o < (unsigned)max_blobs) {
-                    const unsigned long long A2 = sm.acc[4 * k], SX6 = sm.acc[4 * k + 1], SY6 = sm.acc[4 * k + 2];
+                    const unsigned long long A2 = acc_get<WIDE>(sm.acc, 4 * k), SX6 = acc_get<WIDE>(sm.acc, 4 * k + 1), SY6 = acc_get<WIDE>(sm.acc, 4 * k + 2);
                     const double m00 = (double)A2 * 0.5;                       // cv.moments: a00 * 0.5
                     const double m10 = (double)SX6 * 0.16666666666666666;      //             a10 * (1/6)
                     const double m01 = (double)SY6 * 0.16666666666666666;
@@ -420,7 +463,7 @@ __device__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int W, int H, in
                     out_xy[2 * o + 1] = (int)(m01 / m00);
                     if (out_mom) {
                         out_mom[4 * o + 0] = (int64_t)A2; out_mom[4 * o + 1] = (int64_t)SX6;
-                        out_mom[4 * o + 2] = (int64_t)SY6; out_mom[4 * o + 3] = (int64_t)sm.acc[4 * k + 3];
+                        out_mom[4 * o + 2] = (int64_t)SY6; out_mom[4 * o + 3] = (int64_t)acc_get<WIDE>(sm.acc, 4 * k + 3);
                     }
                 }
             }
@@ -447,7 +490,7 @@ struct WarpSlab {
     uint16_t base[BLOB_WE], node_seg[BLOB_WE], node_bits[BLOB_WE], rank[BLOB_WE];
 };
 
-template <int WPB>
+template <int WPB, bool WIDE>
 __global__ void __launch_bounds__(WPB * 32)
 k_blob_reduce_warp(uint32_t* __restrict__ seg_count, const uint32_t* __restrict__ seg_list, int n_images, int E,
                    int W, int H, int max_blobs, int32_t* __restrict__ blob_xy, int32_t* __restrict__ blob_n,
@@ -472,7 +515,7 @@ k_blob_reduce_warp(uint32_t* __restrict__ seg_count, const uint32_t* __restrict_
         const uint32_t* src = seg_list + (size_t)img * E;
         for (int i = lane; i < (int)cnt; i += 32) sm.seg[i] = src[i];
         __syncwarp();
-        ok = blob_reduce<32, true>(sm, (int)cnt, BLOB_WE, BLOB_WACC, W, H, max_blobs, blob_xy + (size_t)img * max_blobs * 2,
+        ok = blob_reduce<32, true, WIDE>(sm, (int)cnt, BLOB_WE, BLOB_WACC, W, H, max_blobs, blob_xy + (size_t)img * max_blobs * 2,
                                    blob_n + img, blob_mom ? blob_mom + (size_t)img * max_blobs * 4 : nullptr, ofl, 0);
     }
     if (lane == 0) {
@@ -482,7 +525,7 @@ k_blob_reduce_warp(uint32_t* __restrict__ seg_count, const uint32_t* __restrict_
 }
 
 // Full-size reduction for the images the warp kernel deferred: persistent CTAs walk the worklist.
-template <int NT>
+template <int NT, bool WIDE>
 __global__ void __launch_bounds__(NT)
 k_blob_reduce(uint32_t* __restrict__ seg_count, const uint32_t* __restrict__ seg_list, int E, int W, int H,
               int max_blobs, int32_t* __restrict__ blob_xy, int32_t* __restrict__ blob_n,
@@ -507,7 +550,7 @@ k_blob_reduce(uint32_t* __restrict__ seg_count, const uint32_t* __restrict__ seg
         const uint32_t* src = seg_list + (size_t)img * E;
         for (int i = threadIdx.x; i < n; i += NT) sm.seg[i] = src[i];
         __syncthreads();
-        blob_reduce<NT, false>(sm, n, E, MOCAP_ACC_CAP, W, H, max_blobs, blob_xy + (size_t)img * max_blobs * 2, blob_n + img,
+        blob_reduce<NT, false, WIDE>(sm, n, E, MOCAP_ACC_CAP, W, H, max_blobs, blob_xy + (size_t)img * max_blobs * 2, blob_n + img,
                                blob_mom ? blob_mom + (size_t)img * max_blobs * 4 : nullptr, ofl, flags);
         __syncthreads();
     }
@@ -561,16 +604,28 @@ int launch_detect(mocap_ctx* ctx, const uint8_t* frames, int n_images, int chann
         ctx->tim_used += 1;
     }
     constexpr int WPB = 8;
-    k_blob_reduce_warp<WPB><<<(n_images + WPB - 1) / WPB, WPB * 32, 0, ctx->stream>>>(
-        ctx->d_seg_count, ctx->d_seg_list, n_images, E, c.width, c.height, c.max_blobs, blob_xy, blob_n, blob_mom, img_flags,
-        ctx->d_worklist, ctx->d_work_count);
-    CUDA_TRY(ctx, cudaGetLastError());
     constexpr int NT = 128;
     const size_t smem = blob_reduce_smem_bytes(E);
     const int grid2 = n_images < ctx->num_sms ? n_images : ctx->num_sms;
-    k_blob_reduce<NT><<<grid2, NT, smem, ctx->stream>>>(ctx->d_seg_count, ctx->d_seg_list, E, c.width, c.height,
-                                                       c.max_blobs, blob_xy, blob_n, blob_mom, img_flags,
-                                                       ctx->d_worklist, ctx->d_work_count, ctx->d_work_count + 1);
+    const long long mx = c.width > c.height ? c.width : c.height;
+    const bool wide = 6ll * mx * c.width * c.height >= (1ll << 32);      // moment sums may exceed 32 bits
+    if (wide) {
+        k_blob_reduce_warp<WPB, true><<<(n_images + WPB - 1) / WPB, WPB * 32, 0, ctx->stream>>>(
+            ctx->d_seg_count, ctx->d_seg_list, n_images, E, c.width, c.height, c.max_blobs, blob_xy, blob_n, blob_mom, img_flags,
+            ctx->d_worklist, ctx->d_work_count);
+        CUDA_TRY(ctx, cudaGetLastError());
+        k_blob_reduce<NT, true><<<grid2, NT, smem, ctx->stream>>>(ctx->d_seg_count, ctx->d_seg_list, E, c.width, c.height,
+                                                               c.max_blobs, blob_xy, blob_n, blob_mom, img_flags,
+                                                               ctx->d_worklist, ctx->d_work_count, ctx->d_work_count + 1);
+    } else {
+        k_blob_reduce_warp<WPB, false><<<(n_images + WPB - 1) / WPB, WPB * 32, 0, ctx->stream>>>(
+            ctx->d_seg_count, ctx->d_seg_list, n_images, E, c.width, c.height, c.max_blobs, blob_xy, blob_n, blob_mom, img_flags,
+            ctx->d_worklist, ctx->d_work_count);
+        CUDA_TRY(ctx, cudaGetLastError());
+        k_blob_reduce<NT, false><<<grid2, NT, smem, ctx->stream>>>(ctx->d_seg_count, ctx->d_seg_list, E, c.width, c.height,
+                                                                c.max_blobs, blob_xy, blob_n, blob_mom, img_flags,
+                                                                ctx->d_worklist, ctx->d_work_count, ctx->d_work_count + 1);
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 1;
     ctx->launches += 2;
@@ -591,6 +646,7 @@ int timing_flush(mocap_ctx* ctx) {
 
 int blob_kernels_init(mocap_ctx* ctx) {
     const size_t smem = blob_reduce_smem_bytes(ctx->cfg.max_segments);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_blob_reduce<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_blob_reduce<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_blob_reduce<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return MOCAP_OK;
 }

@@ -64,3 +64,40 @@ def all_gather_tracks(rec_local, n_total: int, group=None):
     # frame f lives at [f % world, f // world]  ->  transpose restores global order
     ordered = gathered.permute(1, 0, 2).reshape(per * world, width)
     return ordered[:n_total]
+
+
+class TrackBuffer:
+    """Tracks of one rank's shard in ONE flat device allocation, laid out so that the matcher writes
+    straight into the all-gather send buffer (no pack kernel) and the gathered result is read through
+    views (no reorder copy):  [ obj f64 B*R*3 | err f64 B*R | n i32 B | flags i32 B ]."""
+
+    def __init__(self, n_sets: int, max_roots: int, device):
+        import torch
+        self.B, self.R = n_sets, max_roots
+        self.sizes = [n_sets * max_roots * 3 * 8, n_sets * max_roots * 8, n_sets * 4, n_sets * 4]
+        self.offsets = [0]
+        for sz in self.sizes:
+            self.offsets.append((self.offsets[-1] + sz + 15) // 16 * 16)
+        self.nbytes = self.offsets[-1]
+        self.flat = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        self.views = self._views(self.flat)
+        self.gathered = None
+
+    def _views(self, flat):
+        import torch
+        o, B, R = self.offsets, self.B, self.R
+        return {"obj": flat[o[0]: o[0] + self.sizes[0]].view(torch.float64).view(B, R, 3),
+                "err": flat[o[1]: o[1] + self.sizes[1]].view(torch.float64).view(B, R),
+                "n": flat[o[2]: o[2] + self.sizes[2]].view(torch.int32),
+                "flags": flat[o[3]: o[3] + self.sizes[3]].view(torch.int32)}
+
+    def all_gather(self, group=None):
+        """ONE collective over the raw bytes; returns per-rank views [world] of dicts like ``views``.
+        Global frame-set f lives at rank f % world, local index f // world (round-robin ownership)."""
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        if self.gathered is None or self.gathered.shape[0] != world:
+            self.gathered = torch.empty((world, self.nbytes), dtype=torch.uint8, device=self.flat.device)
+        dist.all_gather_into_tensor(self.gathered.view(-1), self.flat, group=group)
+        return [self._views(self.gathered[r]) for r in range(world)]

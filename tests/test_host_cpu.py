@@ -80,6 +80,14 @@ for n_total in (9, 10):
     full = sharding.all_gather_tracks(rec, n_total)
     o2, e2, n2 = sharding.unpack_tracks(full, R)
     assert torch.equal(o2, obj) and torch.equal(e2, err) and torch.equal(n2, n), "gather mismatch"
+    # flat-buffer form: one collective over raw bytes, views on the result
+    if n_total % world == 0:
+        tb = sharding.TrackBuffer(n_total // world, R, "cpu")
+        tb.views["obj"].copy_(obj[mine]); tb.views["err"].copy_(err[mine]); tb.views["n"].copy_(n[mine])
+        per_rank = tb.all_gather()
+        for f in range(n_total):
+            v = per_rank[f % world]
+            assert torch.equal(v["obj"][f // world], obj[f]) and v["n"][f // world] == n[f], "flat gather mismatch"
 dist.destroy_process_group()
 print("OK", rank)
 """

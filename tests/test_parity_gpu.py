@@ -436,3 +436,29 @@ def test_ba_config5_size(torch):
     U, _, Vt = np.linalg.svd(A.T @ Bm)
     Rm = (U @ Vt)
     assert np.abs(A @ Rm - Bm).max() < 0.02
+
+
+def test_detect_large_image_wide_accumulators(torch):
+    """1024x768: moment sums exceed 32 bits, so the 64-bit accumulator kernels run; irregular blobs far
+    from the origin (largest sums), incl. one wider than a warp's segment budget (full-size fallback)."""
+    from oracle.ref_port import RefPort
+    rng = np.random.default_rng(12)
+    H, W = 768, 1024
+    imgs = np.zeros((3, H, W), np.uint8)
+    for f in range(3):
+        for _ in range(10):
+            cx, cy = rng.integers(W - 200, W - 30), rng.integers(H - 200, H - 30)
+            yy, xx = np.mgrid[-20:21, -20:21]
+            r = rng.uniform(3, 12)
+            disc = (xx * xx + yy * yy) <= r * r
+            ys, xs = np.nonzero(disc)
+            imgs[f, np.clip(cy + ys - 20, 0, H - 1), np.clip(cx + xs - 20, 0, W - 1)] = 255
+        imgs[f, 40:140, 30:700] = 200                    # 100 rows x 42 segments: > 128 segments
+    ctx = pkg.MocapContext(1, W, H, max_blobs=64, max_segments=4096)
+    d = ctx.detect(torch.from_numpy(imgs).cuda())
+    port = RefPort([np.eye(3)])
+    for f in range(3):
+        ref = [p for p in port.find_dot(as3(imgs[f])) if p[0] is not None]
+        k = int(d["n"][f])
+        assert int(d["flags"][f]) == 0
+        assert d["xy"][f, :k].cpu().numpy().tolist() == ref
