@@ -8,6 +8,7 @@
 
 int blob_kernels_init(mocap_ctx* ctx);
 int match_kernels_init(mocap_ctx* ctx);
+int fused_kernel_init(mocap_ctx* ctx);
 
 int mocap_fail(mocap_ctx* ctx, int code, const char* fmt, ...) {
     if (ctx) {
@@ -97,6 +98,11 @@ int mocap_create(mocap_ctx** out, const mocap_config* cfg) {
         if (st) break;
         if ((st = blob_kernels_init(ctx)) != MOCAP_OK) break;
         if ((st = match_kernels_init(ctx)) != MOCAP_OK) break;
+        if ((st = fused_kernel_init(ctx)) != MOCAP_OK) break;
+        {
+            const char* mode = getenv("MOCAP_PIPELINE");      // "split": the three-kernel pipeline (for A/B measurements)
+            ctx->use_fused = (mode && strcmp(mode, "split") == 0) ? 0 : 1;
+        }
     } while (0);
     if (st != MOCAP_OK) { mocap_destroy(ctx); return st; }
     *out = ctx;
@@ -109,6 +115,7 @@ void mocap_destroy(mocap_ctx* ctx) {
     cudaDeviceSynchronize();
     cudaFree(ctx->d_tables);
     cudaFree(ctx->d_seg_count); cudaFree(ctx->d_seg_list); cudaFree(ctx->d_worklist); cudaFree(ctx->d_work_count);
+    cudaFree(ctx->d_set_worklist); cudaFree(ctx->d_img_done); cudaFree(ctx->d_set_done); cudaFree(ctx->d_unit_counter);
     cudaFree(ctx->d_blob_xy); cudaFree(ctx->d_blob_n); cudaFree(ctx->d_img_flags);
     cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
     cudaFree(ctx->d_obj); cudaFree(ctx->d_err); cudaFree(ctx->d_nobj); cudaFree(ctx->d_setflags);
@@ -201,15 +208,21 @@ int mocap_set_world_transform(mocap_ctx* ctx, const double* M) {
 static int ensure_images(mocap_ctx* ctx, int n_images) {
     if (n_images <= ctx->cap_images) return MOCAP_OK;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->d_seg_count); cudaFree(ctx->d_seg_list); cudaFree(ctx->d_worklist); cudaFree(ctx->d_work_count); cudaFree(ctx->d_blob_xy); cudaFree(ctx->d_blob_n); cudaFree(ctx->d_img_flags);
-    ctx->d_seg_count = nullptr; ctx->d_seg_list = nullptr; ctx->d_worklist = nullptr; ctx->d_work_count = nullptr; ctx->d_blob_xy = nullptr; ctx->d_blob_n = nullptr; ctx->d_img_flags = nullptr;
+    cudaFree(ctx->d_seg_count); cudaFree(ctx->d_seg_list); cudaFree(ctx->d_worklist); cudaFree(ctx->d_work_count); cudaFree(ctx->d_set_worklist); cudaFree(ctx->d_img_done); cudaFree(ctx->d_set_done); cudaFree(ctx->d_unit_counter); cudaFree(ctx->d_blob_xy); cudaFree(ctx->d_blob_n); cudaFree(ctx->d_img_flags);
+    ctx->d_seg_count = nullptr; ctx->d_seg_list = nullptr; ctx->d_worklist = nullptr; ctx->d_work_count = nullptr; ctx->d_set_worklist = nullptr; ctx->d_img_done = nullptr; ctx->d_set_done = nullptr; ctx->d_unit_counter = nullptr; ctx->d_blob_xy = nullptr; ctx->d_blob_n = nullptr; ctx->d_img_flags = nullptr;
     ctx->cap_images = 0;
     const size_t n = (size_t)n_images;
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_seg_count, n * sizeof(uint32_t)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_seg_list, n * ctx->cfg.max_segments * sizeof(uint32_t)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_worklist, n * sizeof(uint32_t)));
-    CUDA_TRY(ctx, cudaMalloc(&ctx->d_work_count, 2 * sizeof(uint32_t)));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_work_count, 0, 2 * sizeof(uint32_t), ctx->stream));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_work_count, 4 * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_work_count, 0, 4 * sizeof(uint32_t), ctx->stream));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_set_worklist, n * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_img_done, n * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_set_done, 2 * n * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_unit_counter, sizeof(unsigned long long)));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_img_done, 0, n * sizeof(uint32_t), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_set_done, 0, 2 * n * sizeof(uint32_t), ctx->stream));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_blob_xy, n * ctx->cfg.max_blobs * 2 * sizeof(int32_t)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_blob_n, n * sizeof(int32_t)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_img_flags, n * sizeof(int32_t)));
@@ -267,11 +280,19 @@ int mocap_pipeline_dev(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets, 
     CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
     const int C = ctx->cfg.n_cam;
     const size_t set_bytes = (size_t)C * ctx->cfg.width * ctx->cfg.height * channels;
-    const int chunk = 4096;                       // frame-sets per launch group: bounds the segment-list scratch
+    const bool fused = ctx->use_fused && channels == 1;
+    // frame-sets per launch group: bounds the segment-list scratch (max_segments * 4 B per image)
+    const int chunk = fused ? (65536 / C > 0 ? 65536 / C : 1) : 4096;
     int st = ensure_images(ctx, (n_frame_sets < chunk ? n_frame_sets : chunk) * C);
     if (st) return st;
     for (int s0 = 0; s0 < n_frame_sets; s0 += chunk) {
         const int ns = (n_frame_sets - s0 < chunk) ? n_frame_sets - s0 : chunk;
+        if (fused) {
+            st = launch_pipeline_fused(ctx, frames + (size_t)s0 * set_bytes, ns, threshold, obj + (size_t)s0 * ctx->cfg.max_roots * 3,
+                                       err + (size_t)s0 * ctx->cfg.max_roots, n_obj + s0, set_flags ? set_flags + s0 : nullptr);
+            if (st) return st;
+            continue;
+        }
         st = launch_detect(ctx, frames + (size_t)s0 * set_bytes, ns * C, channels, threshold,
                            ctx->d_blob_xy, ctx->d_blob_n, nullptr, ctx->d_img_flags);
         if (st) return st;
@@ -316,6 +337,13 @@ int mocap_pipeline_host(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets,
                                       cudaMemcpyHostToDevice, ctx->copy_stream));
         CUDA_TRY(ctx, cudaEventRecord(copied, ctx->copy_stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, copied, 0));
+        if (ctx->use_fused && channels == 1) {
+            st = launch_pipeline_fused(ctx, ctx->d_stage[k], ns, threshold, ctx->d_obj + (size_t)s0 * RM * 3, ctx->d_err + (size_t)s0 * RM,
+                                       ctx->d_nobj + s0, ctx->d_setflags + s0);
+            if (st) break;
+            CUDA_TRY(ctx, cudaEventRecord(ctx->stage_free[k], ctx->stream));
+            continue;
+        }
         st = launch_detect(ctx, ctx->d_stage[k], ns * C, channels, threshold, ctx->d_blob_xy, ctx->d_blob_n, nullptr, ctx->d_img_flags);
         if (st) break;
         CUDA_TRY(ctx, cudaEventRecord(ctx->stage_free[k], ctx->stream));

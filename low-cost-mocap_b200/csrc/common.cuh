@@ -39,7 +39,12 @@ struct mocap_ctx {
     uint32_t* d_seg_count;
     uint32_t* d_seg_list;
     uint32_t* d_worklist;     // images deferred by the warp-level blob kernel
-    uint32_t* d_work_count;   // [2]: count, finished-CTA counter
+    uint32_t* d_work_count;   // [4]: image worklist count + finished-CTA counter, set worklist count + finished-CTA counter
+    uint32_t* d_set_worklist; // frame-sets deferred by the fused kernel
+    uint32_t* d_img_done;     // fused kernel: finished units per image (self-resetting)
+    uint32_t* d_set_done;     // fused kernel: [2*cap_images] finished images per set, then deferred marks
+    unsigned long long* d_unit_counter;
+    int       use_fused;      // 1: single fused pipeline kernel for 1-channel frames (default)
     int32_t*  d_blob_xy;
     int32_t*  d_blob_n;
     int32_t*  d_img_flags;
@@ -77,7 +82,10 @@ int launch_match(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n, 
                  double* obj, double* err, int32_t* n_obj, int32_t* set_flags, int32_t* chosen);
 int launch_triangulate(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points,
                        const double* X_in, double* X, double* err, uint8_t* valid);
-size_t blob_reduce_smem_bytes(int max_segments);
-size_t match_smem_bytes(const mocap_config& cfg, int warps);
 int ensure_scratch(mocap_ctx* ctx, size_t bytes);
+int launch_blob_fallback(mocap_ctx* ctx, int32_t* blob_xy, int32_t* blob_n, int64_t* blob_mom, int32_t* img_flags);
+int launch_match_list(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n, const uint32_t* set_list, uint32_t* set_count,
+                      int n_sets_max, double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
+int launch_pipeline_fused(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int threshold,
+                          double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
 int timing_flush(mocap_ctx* ctx);

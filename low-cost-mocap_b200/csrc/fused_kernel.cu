@@ -1,0 +1,212 @@
+// S1 + S2 + S3 in ONE persistent kernel (1-channel frames): the whole per-frame body of
+// Cameras._camera_read (reference computer_code/api/helpers.py:84-103) in a single pass over HBM.
+//
+// Work is claimed dynamically, one "unit" (a contiguous slice of an image) per warp at a time:
+//   stream    the warp thresholds its slice with 8 independent 128-bit streaming loads per lane and
+//             appends the rare non-empty 16-pixel segments to the image's list (as k_threshold_segments)
+//   last one  the warp that completes the LAST slice of an image (atomic counter, release/acquire by
+//   reduces   __threadfence) reduces that image's segment list to blobs right away (warp-level
+//             blob_reduce), while every other warp keeps streaming
+//   last one  the warp that completes the LAST image of a frame-set runs the matcher + DLT +
+//   matches   reprojection error for that frame-set (match_triangulate_warp)
+// Nobody ever waits: there are no inter-warp spin loops, only "last arriver does the follow-up work",
+// so the sparse stages hide under the HBM stream of the other warps of the SM instead of running as
+// separate kernels after it.  Images / frame-sets beyond the warp-level capacities are put on
+// worklists and finished by the full-size kernels (k_blob_reduce, k_match_triangulate) afterwards.
+#include "common.cuh"
+#include "blob_device.cuh"
+#include "match_device.cuh"
+
+#define FUSED_WARPS 8
+#define FUSED_UNROLL 8
+#define FUSED_SEGS_PER_ITER (32 * FUSED_UNROLL)      // 256 segments = 4 KB per warp iteration
+
+struct FusedParams {
+    const uint4* frames;
+    long long total_units;
+    int n_sets, C, W, H;
+    int seg_per_image, units_per_image, iters_per_unit;
+    ThreshConst tc;
+    int E;                         // stride of the global segment lists
+    uint32_t* seg_count; uint32_t* seg_list;
+    uint32_t* img_done;            // [n_images]  finished units per image (self-resetting)
+    uint32_t* set_done;            // [n_sets]    finished images per frame-set (self-resetting)
+    uint32_t* set_defer;           // [n_sets]    != 0: an image of the set went to the worklist
+    unsigned long long* unit_counter;
+    int32_t* blob_xy; int32_t* blob_n; int32_t* img_flags;
+    uint32_t* img_worklist; uint32_t* img_work_count;
+    uint32_t* set_worklist; uint32_t* set_work_count;
+    const CameraTables* tb;
+    int MB, RMAX, KC; uint32_t GMAX;
+    double* obj; double* err; int32_t* n_obj; int32_t* set_flags;
+    size_t slab_bytes;
+};
+
+template <bool WIDE>
+__global__ void __launch_bounds__(FUSED_WARPS * 32, 2)
+k_pipeline_fused(const FusedParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* slab = smem_raw + P.slab_bytes * warp;
+
+    while (true) {
+        unsigned long long u = 0;
+        if (lane == 0) u = atomicAdd(P.unit_counter, 1ull);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= (unsigned long long)P.total_units) break;
+        const int img = (int)(u / P.units_per_image);
+        const int unit = (int)(u - (unsigned long long)img * P.units_per_image);
+
+        // ---- stream this slice of the image -----------------------------------------------------
+        const int s_begin = unit * P.iters_per_unit * FUSED_SEGS_PER_ITER;
+        const int s_end = min(P.seg_per_image, s_begin + P.iters_per_unit * FUSED_SEGS_PER_ITER);
+        const uint4* src = P.frames + (size_t)img * P.seg_per_image;
+        for (int s0 = s_begin; s0 < s_end; s0 += FUSED_SEGS_PER_ITER) {
+            uint4 v[FUSED_UNROLL];
+#pragma unroll
+            for (int q = 0; q < FUSED_UNROLL; ++q) {
+                const int si = s0 + q * 32 + lane;
+                v[q] = (si < s_end) ? ldg_stream(src + si) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int q = 0; q < FUSED_UNROLL; ++q) {
+                const uint32_t h0 = swar_gt(v[q].x, P.tc), h1 = swar_gt(v[q].y, P.tc);
+                const uint32_t h2 = swar_gt(v[q].z, P.tc), h3 = swar_gt(v[q].w, P.tc);
+                if (((h0 | h1 | h2 | h3) & 0x80808080u) == 0) continue;
+                const int si = s0 + q * 32 + lane;
+                const uint32_t m = nibble_of(h0) | (nibble_of(h1) << 4) | (nibble_of(h2) << 8) | (nibble_of(h3) << 12);
+                const uint32_t slot = atomicAdd(&P.seg_count[img], 1u);
+                if (slot < (uint32_t)P.E) P.seg_list[(size_t)img * P.E + slot] = ((uint32_t)si << 16) | m;
+            }
+        }
+        __threadfence();                                   // release: this warp's list entries
+        __syncwarp();
+        unsigned done = 0;
+        if (lane == 0) done = atomicAdd(&P.img_done[img], 1u);
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done != (unsigned)P.units_per_image - 1) continue;
+
+        // ---- this warp finished the image: reduce its segment list to blobs ----------------------
+        __threadfence();                                   // acquire: everybody else's list entries
+        const unsigned cnt = __ldcg(&P.seg_count[img]);
+        bool deferred = false;
+        if (cnt == 0) {
+            if (lane == 0) { P.blob_n[img] = 0; if (P.img_flags) P.img_flags[img] = 0; }
+        } else {
+            bool ok = cnt <= BLOB_WE;
+            if (ok) {
+                WarpSlab& sl = *reinterpret_cast<WarpSlab*>(slab);
+                BlobSmem sm;
+                sm.seg = sl.seg; sm.parent = sl.parent; sm.base = sl.base; sm.node_seg = sl.node_seg;
+                sm.node_bits = sl.node_bits; sm.rank = sl.rank; sm.acc = sl.acc; sm.wsum = nullptr;
+                const uint32_t* lst = P.seg_list + (size_t)img * P.E;
+                for (int i = lane; i < (int)cnt; i += 32) sm.seg[i] = __ldcg(lst + i);
+                __syncwarp();
+                ok = blob_reduce<32, true, WIDE>(sm, (int)cnt, BLOB_WE, BLOB_WACC, P.W, P.H, P.MB,
+                                                 P.blob_xy + (size_t)img * P.MB * 2, P.blob_n + img, nullptr,
+                                                 P.img_flags ? P.img_flags + img : nullptr, 0);
+                __syncwarp();
+            }
+            if (lane == 0) {
+                if (ok) P.seg_count[img] = 0;             // self-cleaning
+                else P.img_worklist[atomicAdd(P.img_work_count, 1u)] = (uint32_t)img;
+            }
+            deferred = !ok;
+        }
+        if (lane == 0) { P.img_done[img] = 0; }
+        const int set = img / P.C;
+        if (deferred && lane == 0) atomicOr(&P.set_defer[set], 1u);
+        __threadfence();                                   // release: blob list of this image
+        __syncwarp();
+        unsigned sd = 0;
+        if (lane == 0) sd = atomicAdd(&P.set_done[set], 1u);
+        sd = __shfl_sync(0xffffffffu, sd, 0);
+        if (sd != (unsigned)P.C - 1) continue;
+
+        // ---- this warp finished the frame-set: match + triangulate --------------------------------
+        __threadfence();                                   // acquire: blob lists of the other cameras
+        const unsigned defer = __ldcg(&P.set_defer[set]);
+        if (lane == 0) { P.set_done[set] = 0; P.set_defer[set] = 0; }
+        if (defer) {
+            if (lane == 0) P.set_worklist[atomicAdd(P.set_work_count, 1u)] = (uint32_t)set;
+            continue;
+        }
+        WarpState ws = carve_warp_state(slab, P.RMAX, P.C, P.KC);
+        match_triangulate_warp(P.tb, ws, P.blob_xy + (size_t)set * P.C * P.MB * 2, P.blob_n + (size_t)set * P.C, set, lane,
+                               P.C, P.MB, P.RMAX, P.KC, P.GMAX, P.obj, P.err, P.n_obj, P.set_flags, nullptr);
+        __syncwarp();
+    }
+}
+
+size_t fused_slab_bytes(const mocap_config& c) {
+    size_t a = sizeof(WarpSlab), b = warp_state_bytes(c.max_roots, c.n_cam, c.max_cands);
+    size_t m = a > b ? a : b;
+    return (m + 15) & ~(size_t)15;
+}
+
+int launch_pipeline_fused(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int threshold,
+                          double* obj, double* err, int32_t* n_obj, int32_t* set_flags) {
+    if (n_sets <= 0) return MOCAP_OK;
+    const mocap_config& c = ctx->cfg;
+    FusedParams P;
+    memset(&P, 0, sizeof(P));
+    P.frames = reinterpret_cast<const uint4*>(frames);
+    P.n_sets = n_sets; P.C = c.n_cam; P.W = c.width; P.H = c.height;
+    P.seg_per_image = c.width * c.height / MOCAP_SEG_PX;
+    const int iters_total = (P.seg_per_image + FUSED_SEGS_PER_ITER - 1) / FUSED_SEGS_PER_ITER;
+    P.units_per_image = (iters_total + 15) / 16;             // ~16 iterations (64 KB) per unit
+    P.iters_per_unit = (iters_total + P.units_per_image - 1) / P.units_per_image;
+    P.total_units = (long long)n_sets * c.n_cam * P.units_per_image;
+    if (threshold < 0) { P.tc.addc = 0x80808080u; P.tc.use_and = 0; }
+    else if (threshold >= 255) { P.tc.addc = 0; P.tc.use_and = 1; }
+    else {
+        const uint32_t T1 = (uint32_t)threshold + 1u;
+        P.tc.use_and = T1 > 128 ? 1u : 0u;
+        P.tc.addc = (T1 > 128 ? 256u - T1 : 128u - T1) * 0x01010101u;
+    }
+    P.E = c.max_segments;
+    P.seg_count = ctx->d_seg_count; P.seg_list = ctx->d_seg_list;
+    P.img_done = ctx->d_img_done; P.set_done = ctx->d_set_done; P.set_defer = ctx->d_set_done + ctx->cap_images;
+    P.unit_counter = ctx->d_unit_counter;
+    P.blob_xy = ctx->d_blob_xy; P.blob_n = ctx->d_blob_n; P.img_flags = ctx->d_img_flags;
+    P.img_worklist = ctx->d_worklist; P.img_work_count = ctx->d_work_count;
+    P.set_worklist = ctx->d_set_worklist; P.set_work_count = ctx->d_work_count + 2;
+    P.tb = ctx->d_tables;
+    P.MB = c.max_blobs; P.RMAX = c.max_roots; P.KC = c.max_cands; P.GMAX = (uint32_t)c.max_groups;
+    P.obj = obj; P.err = err; P.n_obj = n_obj; P.set_flags = set_flags;
+    P.slab_bytes = fused_slab_bytes(c);
+    const size_t smem = P.slab_bytes * FUSED_WARPS;
+    const long long mx = c.width > c.height ? c.width : c.height;
+    const bool wide = 6ll * mx * c.width * c.height >= (1ll << 32);
+
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_unit_counter, 0, sizeof(unsigned long long), ctx->stream));
+    if (ctx->timing_on) {
+        if (ctx->tim_used == 64) { const int st = timing_flush(ctx); if (st) return st; }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->tim_ev[2 * ctx->tim_used], ctx->stream));
+    }
+    const int grid = ctx->num_sms * 2;
+    if (wide) k_pipeline_fused<true><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
+    else k_pipeline_fused<false><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (ctx->timing_on) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->tim_ev[2 * ctx->tim_used + 1], ctx->stream));
+        ctx->tim_used += 1;
+    }
+    ctx->launches += 1;
+    // slow path for whatever exceeded the warp-level capacities (normally nothing: both kernels
+    // read an empty worklist and exit)
+    int st = launch_blob_fallback(ctx, ctx->d_blob_xy, ctx->d_blob_n, nullptr, ctx->d_img_flags);
+    if (st) return st;
+    st = launch_match_list(ctx, ctx->d_blob_xy, ctx->d_blob_n, ctx->d_set_worklist, ctx->d_work_count + 2, n_sets,
+                           obj, err, n_obj, set_flags);
+    if (st) return st;
+    return MOCAP_OK;
+}
+
+int fused_kernel_init(mocap_ctx* ctx) {
+    const size_t smem = fused_slab_bytes(ctx->cfg) * FUSED_WARPS;
+    if (smem > 100 * 1024) return mocap_fail(ctx, MOCAP_EINVAL, "fused pipeline needs %zu bytes of shared memory per CTA; lower max_roots/max_cands", smem);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return MOCAP_OK;
+}

@@ -15,294 +15,37 @@
 // and enumerates group indices; nothing is materialised.
 #include "common.cuh"
 #include "geom.cuh"
-
-#define FULL_MASK 0xffffffffu
-
-struct WarpState {
-    uint8_t* rcam;     // [RMAX] camera of the root
-    uint8_t* rpt;      // [RMAX] blob index of the root in its camera
-    uint8_t* ncand;    // [RMAX][C]
-    uint8_t* cand;     // [RMAX][C][KC] blob indices sorted by distance to the root's epipolar line
-    uint32_t* gcount;  // [RMAX] number of candidate groups (0: root has < 2 views)
-    uint32_t* gprefix; // [RMAX+1]
-    unsigned long long* best_key;  // [RMAX]
-    uint32_t* best_g;  // [RMAX]
-    double* best_xe;   // [RMAX][4]  X and error of the best group so far
-};
-
-static __host__ __device__ size_t warp_state_bytes(int RMAX, int C, int KC) {
-    size_t b = 0;
-    b += (size_t)RMAX * 32;                      // best_xe
-    b += (size_t)RMAX * 8;                       // best_key
-    b += (size_t)RMAX * 4 * 2 + (RMAX + 1) * 4;  // gcount, best_g, gprefix
-    b += (size_t)RMAX * 2;                       // rcam, rpt
-    b += (size_t)RMAX * C;                       // ncand
-    b += (size_t)RMAX * C * KC;                  // cand
-    return (b + 15) & ~(size_t)15;
-}
-size_t match_smem_bytes(const mocap_config& cfg, int warps) {
-    return warp_state_bytes(cfg.max_roots, cfg.n_cam, cfg.max_cands) * warps;
-}
-__device__ __forceinline__ WarpState carve_warp_state(unsigned char* raw, int RMAX, int C, int KC) {
-    WarpState s;
-    s.best_xe = reinterpret_cast<double*>(raw);              raw += (size_t)RMAX * 32;
-    s.best_key = reinterpret_cast<unsigned long long*>(raw); raw += (size_t)RMAX * 8;
-    s.gcount = reinterpret_cast<uint32_t*>(raw);             raw += (size_t)RMAX * 4;
-    s.best_g = reinterpret_cast<uint32_t*>(raw);             raw += (size_t)RMAX * 4;
-    s.gprefix = reinterpret_cast<uint32_t*>(raw);            raw += (size_t)(RMAX + 1) * 4;
-    s.rcam = raw;                                            raw += RMAX;
-    s.rpt = raw;                                             raw += RMAX;
-    s.ncand = raw;                                           raw += (size_t)RMAX * C;
-    s.cand = raw;
-    return s;
-}
-
-// error -> ordered integer key.  np.argmin treats NaN as the minimum (first NaN wins).
-__device__ __forceinline__ unsigned long long err_key(double e) {
-    if (e != e) return 0ull;
-    return (unsigned long long)__double_as_longlong(e) + 1ull;    // e >= 0
-}
-
-// views of group g of root r: the root's own blob plus, per later camera with candidates, the
-// candidate selected by g's mixed-radix digit (earliest camera = least significant digit)
-__device__ __forceinline__ int decode_group(const WarpState& ws, int C, int KC, int r, uint32_t g,
-                                            int cams[MOCAP_MAX_CAM], int pts[MOCAP_MAX_CAM]) {
-    const int rc = ws.rcam[r];
-    cams[0] = rc; pts[0] = ws.rpt[r];
-    int nv = 1;
-    uint32_t rem = g;
-    for (int i = rc + 1; i < C; ++i) {
-        const int k = ws.ncand[r * C + i];
-        if (k > 0) {
-            const int d = rem % k;
-            rem /= k;
-            cams[nv] = i;
-            pts[nv] = ws.cand[((size_t)r * C + i) * KC + d];
-            ++nv;
-        }
-    }
-    return nv;
-}
-
-// DLT + reprojection error of group g of root r.
-__device__ __forceinline__ void eval_group(const CameraTables* __restrict__ tb, const WarpState& ws,
-                                           const int32_t* __restrict__ xy, int MB, int C, int KC,
-                                           int r, uint32_t g, double X[3], double& err) {
-    Sym4 B;
-    sym4_zero(B);
-    int cams[MOCAP_MAX_CAM];
-    int pts[MOCAP_MAX_CAM];
-    const int nv = decode_group(ws, C, KC, r, g, cams, pts);
-    for (int k = 0; k < nv; ++k) {
-        const int c = cams[k];
-        const double px = (double)xy[((size_t)c * MB + pts[k]) * 2 + 0];
-        const double py = (double)xy[((size_t)c * MB + pts[k]) * 2 + 1];
-        dlt_add_view(B, tb->Pkc[k][c], px, py);      // K of the k-th PRESENT view (helpers.py:305-307)
-    }
-    dlt_solve(B, X);
-    double sq[2 * MOCAP_MAX_CAM];
-    for (int k = 0; k < nv; ++k) {
-        const int c = cams[k];
-        float u, v;
-        project_like_cv(tb->R[c], tb->t[c], tb->fx[k], tb->fy[k], tb->cx[k], tb->cy[k], X, u, v);
-        const double dx = DSUB((double)xy[((size_t)c * MB + pts[k]) * 2 + 0], (double)u);
-        const double dy = DSUB((double)xy[((size_t)c * MB + pts[k]) * 2 + 1], (double)v);
-        sq[2 * k] = DMUL(dx, dx);
-        sq[2 * k + 1] = DMUL(dy, dy);
-    }
-    // a group without None entries is an int64 array in the reference (pairwise float64 sum);
-    // any None turns it into an object array (left fold)
-    err = mean_like_numpy(sq, 2 * nv, nv == C);
-}
+#include "match_device.cuh"
 
 __global__ void __launch_bounds__(128)
-k_match_triangulate(const CameraTables* __restrict__ tb, const int32_t* __restrict__ blob_xy,
-                    const int32_t* __restrict__ blob_n, int n_sets, int C, int MB, int RMAX, int KC,
+k_match_triangulate(const CameraTables* __restrict__ tb, const int32_t* blob_xy, const int32_t* blob_n,
+                    const uint32_t* __restrict__ set_list, uint32_t* set_count,
+                    int n_sets, int C, int MB, int RMAX, int KC,
                     uint32_t GMAX, double* __restrict__ obj, double* __restrict__ err_out,
                     int32_t* __restrict__ n_obj, int32_t* __restrict__ set_flags, int32_t* __restrict__ chosen) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warps = blockDim.x >> 5;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpState ws = carve_warp_state(smem_raw + warp_state_bytes(RMAX, C, KC) * wid, RMAX, C, KC);
+    if (set_list) {                                   // persistent walk over a worklist of frame-sets
+        const unsigned n_work = *set_count;
+        for (unsigned w = blockIdx.x * warps + wid; w < n_work; w += gridDim.x * warps) {
+            const int set = (int)set_list[w];
+            match_triangulate_warp(tb, ws, blob_xy + (size_t)set * C * MB * 2, blob_n + (size_t)set * C, set, lane,
+                                   C, MB, RMAX, KC, GMAX, obj, err_out, n_obj, set_flags, chosen);
+            __syncwarp();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {                           // the last CTA to finish re-arms the worklist
+            __threadfence();
+            if (atomicAdd(set_count + 1, 1u) == gridDim.x - 1) { set_count[0] = 0; set_count[1] = 0; }
+        }
+        return;
+    }
     const int set = blockIdx.x * warps + wid;
     if (set >= n_sets) return;
-    WarpState ws = carve_warp_state(smem_raw + warp_state_bytes(RMAX, C, KC) * wid, RMAX, C, KC);
-    const int32_t* xy = blob_xy + (size_t)set * C * MB * 2;
-    const int32_t* nb = blob_n + (size_t)set * C;
-    int flags = 0;
-
-    // roots from camera 0 (helpers.py:349,357)
-    int nr = min(nb[0], MB);
-    if (nr > RMAX) { nr = RMAX; flags |= MOCAP_F_ROOTS; }
-    for (int r = lane; r < RMAX; r += 32) {
-        if (r < nr) { ws.rcam[r] = 0; ws.rpt[r] = (uint8_t)r; }
-        for (int i = 0; i < C; ++i) ws.ncand[r * C + i] = 0;
-    }
-    __syncwarp();
-
-    for (int i = 1; i < C; ++i) {                              // helpers.py:359
-        const int ni = min(nb[i], MB);
-        unsigned long long matched = 0ull;                     // "closest match" blobs of camera i
-        for (int j = lane; j < nr; j += 32) {                  // roots that exist before camera i
-            const int rc = ws.rcam[j];
-            const double rx = (double)xy[((size_t)rc * MB + ws.rpt[j]) * 2 + 0];
-            const double ry = (double)xy[((size_t)rc * MB + ws.rpt[j]) * 2 + 1];
-            const double* F = tb->F[rc][i];
-            // cv.computeCorrespondEpilines on a float32 point: double math, float32 result (helpers.py:363-364)
-            double a = DADD(DADD(DMUL(F[0], rx), DMUL(F[1], ry)), F[2]);
-            double b = DADD(DADD(DMUL(F[3], rx), DMUL(F[4], ry)), F[5]);
-            double c = DADD(DADD(DMUL(F[6], rx), DMUL(F[7], ry)), F[8]);
-            double nu = DADD(DMUL(a, a), DMUL(b, b));
-            nu = (nu != 0.0) ? 1.0 / sqrt(nu) : 1.0;
-            a = (double)(float)DMUL(a, nu);
-            b = (double)(float)DMUL(b, nu);
-            c = (double)(float)DMUL(c, nu);
-            const double den = sqrt(DADD(DMUL(a, a), DMUL(b, b)));      // helpers.py:373
-            double dist[MOCAP_MAX_CANDS];
-            uint8_t* cl = ws.cand + ((size_t)j * C + i) * KC;
-            int cnt = 0;
-            for (int q = 0; q < ni; ++q) {
-                const double px = (double)xy[((size_t)i * MB + q) * 2 + 0];
-                const double py = (double)xy[((size_t)i * MB + q) * 2 + 1];
-                const double d = fabs(DADD(DADD(DMUL(a, px), DMUL(b, py)), c)) / den;
-                if (d < 5.0) {                                  // helpers.py:375
-                    if (cnt == KC) {
-                        flags |= MOCAP_F_CANDS;
-                        if (!(d < dist[KC - 1])) continue;
-                        --cnt;
-                    }
-                    int pos = cnt;                              // stable insertion: after every dist <= d
-                    while (pos > 0 && dist[pos - 1] > d) { dist[pos] = dist[pos - 1]; cl[pos] = cl[pos - 1]; --pos; }
-                    dist[pos] = d; cl[pos] = (uint8_t)q;
-                    ++cnt;
-                }
-            }
-            ws.ncand[j * C + i] = (uint8_t)cnt;
-            if (cnt > 0) {                                      // helpers.py:391: drop every row equal to the closest match
-                const int q0 = cl[0];
-                const int cx0 = xy[((size_t)i * MB + q0) * 2 + 0], cy0 = xy[((size_t)i * MB + q0) * 2 + 1];
-                for (int q = 0; q < ni; ++q)
-                    if (xy[((size_t)i * MB + q) * 2 + 0] == cx0 && xy[((size_t)i * MB + q) * 2 + 1] == cy0)
-                        matched |= 1ull << q;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) matched |= __shfl_xor_sync(FULL_MASK, matched, o);
-        // blobs of camera i that were nobody's closest match become roots (helpers.py:402-406)
-        for (int q0 = 0; q0 < ni; q0 += 32) {
-            const int q = q0 + lane;
-            const bool un = q < ni && !((matched >> q) & 1ull);
-            const unsigned bal = __ballot_sync(FULL_MASK, un);
-            const int pos = nr + __popc(bal & ((1u << lane) - 1u));
-            if (un) {
-                if (pos < RMAX) { ws.rcam[pos] = (uint8_t)i; ws.rpt[pos] = (uint8_t)q; }
-                else flags |= MOCAP_F_ROOTS;
-            }
-            nr = min(nr + __popc(bal), RMAX);
-        }
-        __syncwarp();
-    }
-
-    // number of candidate groups of every root
-    for (int r0 = 0; r0 < nr; r0 += 32) {
-        const int r = r0 + lane;
-        uint32_t G = 0;
-        if (r < nr) {
-            unsigned long long prod = 1ull;
-            int views = 1;
-            for (int i = ws.rcam[r] + 1; i < C; ++i) {
-                const int k = ws.ncand[r * C + i];
-                if (k > 0) { prod *= (unsigned long long)k; ++views; if (prod > GMAX) { prod = GMAX; flags |= MOCAP_F_GROUPS; } }
-            }
-            G = views >= 2 ? (uint32_t)prod : 0u;
-            ws.gcount[r] = G;
-            ws.best_key[r] = ~0ull;
-            ws.best_g[r] = 0u;
-        }
-    }
-    __syncwarp();
-    if (lane == 0) {
-        uint32_t acc = 0;
-        for (int r = 0; r < nr; ++r) { ws.gprefix[r] = acc; acc += ws.gcount[r]; }
-        ws.gprefix[nr] = acc;
-    }
-    __syncwarp();
-    const uint32_t total = ws.gprefix[nr];
-
-    // pass 1: every group's point and error; segmented warp argmin; the head lane of every root's
-    // segment pulls the winner's point over by shuffle and folds it into shared memory
-    for (uint32_t w0 = 0; w0 < total; w0 += 32) {
-        const uint32_t w = w0 + lane;
-        int r = -1;
-        uint32_t g = 0;
-        unsigned long long key = ~0ull;
-        double X[3] = {0.0, 0.0, 0.0}, e = 0.0;
-        if (w < total) {
-            int lo = 0, hi = nr;                               // last r with gprefix[r] <= w
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ws.gprefix[mid] <= w) lo = mid; else hi = mid; }
-            r = lo;
-            g = w - ws.gprefix[r];
-            eval_group(tb, ws, xy, MB, C, KC, r, g, X, e);
-            key = err_key(e);
-        }
-        int src = lane;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int r2 = __shfl_down_sync(FULL_MASK, r, o);
-            const uint32_t g2 = __shfl_down_sync(FULL_MASK, g, o);
-            const unsigned long long k2 = __shfl_down_sync(FULL_MASK, key, o);
-            const int s2 = __shfl_down_sync(FULL_MASK, src, o);
-            if (lane + o < 32 && r2 == r && (k2 < key || (k2 == key && g2 < g))) { key = k2; g = g2; src = s2; }
-        }
-        const double bx = __shfl_sync(FULL_MASK, X[0], src), by = __shfl_sync(FULL_MASK, X[1], src);
-        const double bz = __shfl_sync(FULL_MASK, X[2], src), be = __shfl_sync(FULL_MASK, e, src);
-        const int rprev = __shfl_up_sync(FULL_MASK, r, 1);
-        const bool head = (r >= 0) && (lane == 0 || rprev != r);
-        if (head && key < ws.best_key[r]) {                    // ties keep the earlier group (np.argmin)
-            ws.best_key[r] = key; ws.best_g[r] = g;
-            ws.best_xe[4 * r + 0] = bx; ws.best_xe[4 * r + 1] = by; ws.best_xe[4 * r + 2] = bz; ws.best_xe[4 * r + 3] = be;
-        }
-        __syncwarp();
-    }
-
-    // pass 2: winners, compacted in root order (helpers.py:413-419 skips roots without a 3D point)
-    int n_out = 0;
-    double* obj_s = obj + (size_t)set * RMAX * 3;
-    double* err_s = err_out + (size_t)set * RMAX;
-    int32_t* ch_s = chosen ? chosen + (size_t)set * RMAX * C : nullptr;
-    for (int r0 = 0; r0 < nr; r0 += 32) {
-        const int r = r0 + lane;
-        const bool has = r < nr && ws.gcount[r] > 0;
-        const unsigned bal = __ballot_sync(FULL_MASK, has);
-        if (has) {
-            const int o = n_out + __popc(bal & ((1u << lane) - 1u));
-            double X[3] = {ws.best_xe[4 * r], ws.best_xe[4 * r + 1], ws.best_xe[4 * r + 2]};
-            const double e = ws.best_xe[4 * r + 3];
-            if (ch_s) {
-                int cams[MOCAP_MAX_CAM], pts[MOCAP_MAX_CAM];
-                const int nv = decode_group(ws, C, KC, r, ws.best_g[r], cams, pts);
-                for (int i = 0; i < C; ++i) ch_s[(size_t)o * C + i] = -1;
-                for (int k = 0; k < nv; ++k) ch_s[(size_t)o * C + cams[k]] = pts[k];
-            }
-            if (tb->use_world) {                               // helpers.py:96-103
-                const double* M = tb->world;
-                const double x = -X[0], y = -X[1], z = X[2];
-                const double wx = DFMA(M[0], x, DFMA(M[1], y, DFMA(M[2], z, M[3])));
-                const double wy = DFMA(M[4], x, DFMA(M[5], y, DFMA(M[6], z, M[7])));
-                const double wz = DFMA(M[8], x, DFMA(M[9], y, DFMA(M[10], z, M[11])));
-                const double ww = DFMA(M[12], x, DFMA(M[13], y, DFMA(M[14], z, M[15])));
-                X[0] = wx / ww; X[1] = wz / ww; X[2] = wy / ww;
-            }
-            obj_s[3 * o + 0] = X[0]; obj_s[3 * o + 1] = X[1]; obj_s[3 * o + 2] = X[2];
-            err_s[o] = e;
-        }
-        n_out += __popc(bal);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) flags |= __shfl_xor_sync(FULL_MASK, flags, o);
-    if (lane == 0) {
-        n_obj[set] = n_out;
-        if (set_flags) set_flags[set] = flags;
-    }
+    match_triangulate_warp(tb, ws, blob_xy + (size_t)set * C * MB * 2, blob_n + (size_t)set * C, set, lane,
+                           C, MB, RMAX, KC, GMAX, obj, err_out, n_obj, set_flags, chosen);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -361,9 +104,24 @@ int launch_match(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n, 
     const int warps = 4;
     const size_t smem = match_smem_bytes(c, warps);
     const int grid = (n_sets + warps - 1) / warps;
-    k_match_triangulate<<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_tables, blob_xy, blob_n, n_sets, c.n_cam,
+    k_match_triangulate<<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_tables, blob_xy, blob_n, nullptr, nullptr, n_sets, c.n_cam,
                                                                  c.max_blobs, c.max_roots, c.max_cands,
                                                                  (uint32_t)c.max_groups, obj, err, n_obj, set_flags, chosen);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return MOCAP_OK;
+}
+
+int launch_match_list(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n, const uint32_t* set_list, uint32_t* set_count,
+                      int n_sets_max, double* obj, double* err, int32_t* n_obj, int32_t* set_flags) {
+    const mocap_config& c = ctx->cfg;
+    const int warps = 4;
+    const size_t smem = match_smem_bytes(c, warps);
+    int grid = (n_sets_max + warps - 1) / warps;
+    if (grid > ctx->num_sms) grid = ctx->num_sms;
+    k_match_triangulate<<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_tables, blob_xy, blob_n, set_list, set_count, n_sets_max, c.n_cam,
+                                                                 c.max_blobs, c.max_roots, c.max_cands, (uint32_t)c.max_groups,
+                                                                 obj, err, n_obj, set_flags, nullptr);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 1;
     return MOCAP_OK;
