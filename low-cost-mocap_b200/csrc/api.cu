@@ -98,11 +98,11 @@ int mocap_create(mocap_ctx** out, const mocap_config* cfg) {
         if (st) break;
         if ((st = blob_kernels_init(ctx)) != MOCAP_OK) break;
         if ((st = match_kernels_init(ctx)) != MOCAP_OK) break;
-        if ((st = fused_kernel_init(ctx)) != MOCAP_OK) break;
         {
             const char* mode = getenv("MOCAP_PIPELINE");      // "split": the three-kernel pipeline (for A/B measurements)
             ctx->use_fused = (mode && strcmp(mode, "split") == 0) ? 0 : 1;
         }
+        if ((st = fused_kernel_init(ctx)) != MOCAP_OK) break;
     } while (0);
     if (st != MOCAP_OK) { mocap_destroy(ctx); return st; }
     *out = ctx;
