@@ -53,7 +53,7 @@ template <int NT>
 __device__ __forceinline__ unsigned block_scan_excl(unsigned v, unsigned& total, unsigned* wsum) {
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned x = v;
-#pragma unroll
+#pragma unroll 1
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= (unsigned)o) x += y;
@@ -152,7 +152,7 @@ __device__ __forceinline__ unsigned long long acc_get(const unsigned long long* 
 // Returns false (group-uniform) without writing anything when STRICT and a capacity (runs > E,
 // blobs > ACC) is exceeded: the caller then hands the image to the full-size kernel.
 template <int NT, bool STRICT, bool WIDE>
-__device__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int W, int H, int max_blobs,
+__device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int W, int H, int max_blobs,
                             int32_t* __restrict__ out_xy, int32_t* __restrict__ out_n,
                             int64_t* __restrict__ out_mom, int32_t* __restrict__ out_flags, int flags_in) {
     const int tid = threadIdx.x % NT;

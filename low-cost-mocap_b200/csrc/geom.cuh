@@ -115,10 +115,30 @@ GEOM_HD void sym4_null_vector(const Sym4& B, double out[4]) {
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) v[r][c] = (r == c) ? 1.0 : 0.0;
+    // Tournament order: rounds {(0,1),(2,3)}, {(0,2),(1,3)}, {(0,3),(1,2)}.  Only the first round is
+    // written out; the other two are the same code after relabelling the indices by the cycle
+    // 1 -> 2 -> 3 -> 1 (register moves), which returns to the identity after three rounds.  Keeps the
+    // instruction footprint at two rotation bodies instead of six (the kernels are I-cache bound).
+#pragma unroll 1
     for (int sweep = 0; sweep < 30; ++sweep) {
         const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[0][3]) + fabs(a[1][2]) + fabs(a[1][3]) + fabs(a[2][3]);
         if (off == 0.0) break;
-        JROT(0, 1) JROT(0, 2) JROT(0, 3) JROT(1, 2) JROT(1, 3) JROT(2, 3)
+#pragma unroll 1
+        for (int round = 0; round < 3; ++round) {
+            JROT(0, 1) JROT(2, 3)
+            // relabel: new[i][j] = old[rho(i)][rho(j)], rho = (0, 2, 3, 1)
+            const double n01 = a[0][2], n02 = a[0][3], n03 = a[0][1];
+            const double n11 = a[2][2], n12 = a[2][3], n13 = a[1][2];
+            const double n22 = a[3][3], n23 = a[1][3], n33 = a[1][1];
+            a[0][1] = n01; a[0][2] = n02; a[0][3] = n03;
+            a[1][1] = n11; a[1][2] = n12; a[1][3] = n13;
+            a[2][2] = n22; a[2][3] = n23; a[3][3] = n33;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double c1 = v[r][2], c2 = v[r][3], c3 = v[r][1];
+                v[r][1] = c1; v[r][2] = c2; v[r][3] = c3;
+            }
+        }
     }
     int best = 0;
     double bv = fabs(a[0][0]);
@@ -164,10 +184,14 @@ GEOM_HD double mean_like_numpy(const double* sq, int n, bool pairwise) {
         else { for (int i = 0; i < n; ++i) res = DADD(res, sq[i]); }
     } else {
         double r[8];
+#pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = sq[j];
         int i = 8;
-        for (; i < n - (n % 8); i += 8)
+#pragma unroll 1
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
             for (int j = 0; j < 8; ++j) r[j] = DADD(r[j], sq[i + j]);
+        }
         res = DADD(DADD(DADD(r[0], r[1]), DADD(r[2], r[3])), DADD(DADD(r[4], r[5]), DADD(r[6], r[7])));
         for (; i < n; ++i) res = DADD(res, sq[i]);
     }

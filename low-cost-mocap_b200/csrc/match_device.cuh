@@ -73,7 +73,7 @@ __device__ __forceinline__ int decode_group(const WarpState& ws, int C, int KC, 
 }
 
 // DLT + reprojection error of group g of root r.
-__device__ __forceinline__ void eval_group(const CameraTables* __restrict__ tb, const WarpState& ws,
+static __device__ __noinline__ void eval_group(const CameraTables* __restrict__ tb, const WarpState& ws,
                                            const int32_t* xy, int MB, int C, int KC,
                                            int r, uint32_t g, double X[3], double& err) {
     Sym4 B;
@@ -81,6 +81,7 @@ __device__ __forceinline__ void eval_group(const CameraTables* __restrict__ tb, 
     int cams[MOCAP_MAX_CAM];
     int pts[MOCAP_MAX_CAM];
     const int nv = decode_group(ws, C, KC, r, g, cams, pts);
+#pragma unroll 1
     for (int k = 0; k < nv; ++k) {
         const int c = cams[k];
         const double px = (double)__ldcg(xy + ((size_t)c * MB + pts[k]) * 2 + 0);
@@ -89,6 +90,7 @@ __device__ __forceinline__ void eval_group(const CameraTables* __restrict__ tb, 
     }
     dlt_solve(B, X);
     double sq[2 * MOCAP_MAX_CAM];
+#pragma unroll 1
     for (int k = 0; k < nv; ++k) {
         const int c = cams[k];
         float u, v;
@@ -105,7 +107,7 @@ __device__ __forceinline__ void eval_group(const CameraTables* __restrict__ tb, 
 
 // One warp: the whole matcher for frame-set `set`.  xy / nb are read with ld.global.cg so that the
 // function may consume blob lists written earlier IN THE SAME KERNEL by other warps (fused pipeline).
-__device__ __forceinline__ void match_triangulate_warp(
+static __device__ __noinline__ void match_triangulate_warp(
     const CameraTables* __restrict__ tb, WarpState ws, const int32_t* xy, const int32_t* nb, int set, int lane,
     int C, int MB, int RMAX, int KC, uint32_t GMAX, double* __restrict__ obj, double* __restrict__ err_out,
     int32_t* __restrict__ n_obj, int32_t* __restrict__ set_flags, int32_t* __restrict__ chosen) {
@@ -141,6 +143,7 @@ __device__ __forceinline__ void match_triangulate_warp(
             double dist[MOCAP_MAX_CANDS];
             uint8_t* cl = ws.cand + ((size_t)j * C + i) * KC;
             int cnt = 0;
+#pragma unroll 1
             for (int q = 0; q < ni; ++q) {
                 const double px = (double)__ldcg(xy + ((size_t)i * MB + q) * 2 + 0);
                 const double py = (double)__ldcg(xy + ((size_t)i * MB + q) * 2 + 1);
@@ -166,7 +169,7 @@ __device__ __forceinline__ void match_triangulate_warp(
                         matched |= 1ull << q;
             }
         }
-#pragma unroll
+#pragma unroll 1
         for (int o = 16; o > 0; o >>= 1) matched |= __shfl_xor_sync(FULL_MASK, matched, o);
         // blobs of camera i that were nobody's closest match become roots (helpers.py:402-406)
         for (int q0 = 0; q0 < ni; q0 += 32) {
@@ -226,7 +229,7 @@ __device__ __forceinline__ void match_triangulate_warp(
             key = err_key(e);
         }
         int src = lane;
-#pragma unroll
+#pragma unroll 1
         for (int o = 1; o < 32; o <<= 1) {
             const int r2 = __shfl_down_sync(FULL_MASK, r, o);
             const uint32_t g2 = __shfl_down_sync(FULL_MASK, g, o);
@@ -278,7 +281,7 @@ __device__ __forceinline__ void match_triangulate_warp(
         }
         n_out += __popc(bal);
     }
-#pragma unroll
+#pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) flags |= __shfl_xor_sync(FULL_MASK, flags, o);
     if (lane == 0) {
         n_obj[set] = n_out;
