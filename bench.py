@@ -271,6 +271,8 @@ def run_gpu_arm(args):
     d2h = sum(v.numel() * v.element_size() for v in host_out.values())
     same = bool((host_out["n"].to(dev) == out["n"]).all().item())
 
+    kernel_name = ("k_threshold_segments_c1 (three-kernel pipeline)" if os.environ.get("MOCAP_PIPELINE") == "split"
+                   else "k_pipeline_fused (threshold + blob reduce + match/DLT in one pass)")
     if rank == 0:
         peak, peak_src = measured_peak()
         # algorithmic bytes: C*W*H bytes per frame-set, read exactly once; a step is split into
@@ -301,7 +303,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": "frame-sets/s", "h2d_bytes_per_step": int(bytes_per_step),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "matches_resident_path": same},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_threshold_segments_c1", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes) if alg_bytes else None,
                          "avg_launch_ms": kern_ms, "launches_timed": kern_n,

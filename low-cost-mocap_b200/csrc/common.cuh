@@ -44,6 +44,7 @@ struct mocap_ctx {
     uint32_t* d_img_done;     // fused kernel: finished units per image (self-resetting)
     uint32_t* d_set_done;     // fused kernel: [2*cap_images] finished images per set, then deferred marks
     unsigned long long* d_unit_counter;
+    int       fused_ctas_per_sm;
     int       use_fused;      // 1: single fused pipeline kernel for 1-channel frames (default)
     int32_t*  d_blob_xy;
     int32_t*  d_blob_n;

@@ -43,7 +43,7 @@ struct FusedParams {
 };
 
 template <bool WIDE>
-__global__ void __launch_bounds__(FUSED_WARPS * 32, 2)
+__global__ void __launch_bounds__(FUSED_WARPS * 32, 4)
 k_pipeline_fused(const FusedParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -190,7 +190,7 @@ int launch_pipeline_fused(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int
         if (ctx->tim_used == 64) { const int st = timing_flush(ctx); if (st) return st; }
         CUDA_TRY(ctx, cudaEventRecord(ctx->tim_ev[2 * ctx->tim_used], ctx->stream));
     }
-    const int grid = ctx->num_sms * 2;
+    const int grid = ctx->num_sms * ctx->fused_ctas_per_sm;
     if (wide) k_pipeline_fused<true><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
     else k_pipeline_fused<false><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
     CUDA_TRY(ctx, cudaGetLastError());
@@ -211,8 +211,12 @@ int launch_pipeline_fused(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int
 
 int fused_kernel_init(mocap_ctx* ctx) {
     const size_t smem = fused_slab_bytes(ctx->cfg) * FUSED_WARPS;
-    if (smem > 110 * 1024) { ctx->use_fused = 0; return MOCAP_OK; }     // matcher state too large for 2 CTAs per SM: three-kernel pipeline
+    if (smem > 110 * 1024) { ctx->use_fused = 0; return MOCAP_OK; }    // matcher state too large: three-kernel pipeline
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;      // persistent grid = what is actually co-resident
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipeline_fused<false>, FUSED_WARPS * 32, smem));
+    if (per_sm < 1) { ctx->use_fused = 0; return MOCAP_OK; }
+    ctx->fused_ctas_per_sm = per_sm;
     return MOCAP_OK;
 }
