@@ -136,6 +136,16 @@ MOCAP_API int mocap_pipeline_dev(mocap_ctx* ctx, const uint8_t* frames, int n_fr
 MOCAP_API int mocap_pipeline_host(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets, int channels,
                         int threshold, double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
 
+/* Tracking hand-off -- replaces locate_objects (helpers.py:424-480) for n_frame_sets frame-sets at
+ * once: marker triplets (two markers 0.15 apart, a third 0.095 from both, tolerance 0.025) -> object
+ * records.  Input is the matcher's output (obj/err/n_obj, with the world transform set if the caller
+ * wants world coordinates as the reference does).  objects double [n_frame_sets][max_objects][5] =
+ * {x, y, z, heading, error}; drone_index int32 [n_frame_sets][max_objects]; n_objects int32
+ * [n_frame_sets].  DEVICE pointers. */
+MOCAP_API int mocap_locate_objects_dev(mocap_ctx* ctx, const double* obj, const double* err, const int32_t* n_obj,
+                             int n_frame_sets, int max_objects, double* objects, int32_t* drone_index,
+                             int32_t* n_objects);
+
 /* S3 -- replaces triangulate_points (helpers.py:330-336) and
  * calculate_reprojection_errors (helpers.py:203-211) on explicit correspondences.
  * obs double [n_points][n_cam][2], mask uint8 [n_points][n_cam] (0 = [None, None]).

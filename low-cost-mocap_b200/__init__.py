@@ -17,5 +17,6 @@ from .api import (  # noqa: F401
     calculate_reprojection_error,
     calculate_reprojection_errors,
     bundle_adjustment,
+    locate_objects,
     install_into,
 )

@@ -184,6 +184,19 @@ class MocapContext:
                                                  _ptr(out["obj"]), _ptr(out["err"]), _ptr(out["n"]), _ptr(out["flags"])))
         return out
 
+    def locate_objects(self, obj, err, n, max_objects=8):
+        """obj f64 [B, max_roots, 3], err f64 [B, max_roots], n int32 [B] (matcher output, cuda tensors) ->
+        dict: objects f64 [B, max_objects, 5] = x y z heading error, drone_index int32 [B, max_objects], n int32 [B]."""
+        torch = _torch()
+        B = n.numel()
+        dev = obj.device
+        out = torch.empty((B, max_objects, 5), dtype=torch.float64, device=dev)
+        di = torch.empty((B, max_objects), dtype=torch.int32, device=dev)
+        cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+        self.use_current_stream()
+        self._check(self.lib.mocap_locate_objects_dev(self.h, _ptr(obj), _ptr(err), _ptr(n), B, max_objects, _ptr(out), _ptr(di), _ptr(cnt)))
+        return {"objects": out, "drone_index": di, "n": cnt}
+
     # -- explicit correspondences (host arrays) -------------------------------------------
     def triangulate(self, obs, mask, want_err=True):
         """obs float64 [F, C, 2], mask uint8 [F, C] -> (X [F,3], err [F] or None, valid [F])."""
@@ -404,6 +417,31 @@ def find_point_correspondance_and_object_points(image_points, camera_poses, fram
     return errors, object_points, frames
 
 
+def locate_objects(object_points, errors, session=None):
+    """Mirror of helpers.py:424-480: list of {"pos": ndarray(3), "heading", "error", "droneIndex"}."""
+    torch = _torch()
+    s = session or MocapSession.default()
+    pts = np.asarray(object_points, dtype=np.float64).reshape(-1, 3)
+    errs = np.asarray(errors, dtype=np.float64).reshape(-1)
+    K = pts.shape[0]
+    if K == 0:
+        return []
+    with s._lock:
+        ctx = s.ctx(len(s.intrinsics))
+        R = ctx.cfg.max_roots
+        if K > R:
+            raise MocapError(-1, f"{K} points; context keeps {R}")
+        obj = np.zeros((1, R, 3)); err = np.zeros((1, R))
+        obj[0, :K] = pts; err[0, :K] = errs
+        d = ctx.locate_objects(torch.from_numpy(obj).to(ctx.torch_device), torch.from_numpy(err).to(ctx.torch_device),
+                               torch.tensor([K], dtype=torch.int32, device=ctx.torch_device), max_objects=max(1, K // 3))
+        k = int(d["n"][0].item())
+        rec = d["objects"][0, :k].cpu().numpy()
+        di = d["drone_index"][0, :k].cpu().numpy()
+    return [{"pos": rec[i, :3].copy(), "heading": float(rec[i, 3]), "error": float(rec[i, 4]), "droneIndex": int(di[i])}
+            for i in range(k)]
+
+
 def bundle_adjustment(image_points, camera_poses, socketio, session=None):
     """Mirror of helpers.py:244-290: returns the list of ``{"R": ndarray 3x3, "t": ndarray (3,)}``.
     ``socketio.emit("camera-pose", ...)`` fires once with the result (the reference emits on
@@ -429,4 +467,5 @@ def install_into(helpers_module, session=None):
     helpers_module.find_point_correspondance_and_object_points = \
         lambda ip, cp, fr: find_point_correspondance_and_object_points(ip, cp, fr, s)
     helpers_module.bundle_adjustment = lambda ip, cp, sio: bundle_adjustment(ip, cp, sio, s)
+    helpers_module.locate_objects = lambda op, er: locate_objects(op, er, s)
     return s

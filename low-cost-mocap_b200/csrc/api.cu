@@ -362,6 +362,15 @@ int mocap_pipeline_host(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets,
     return MOCAP_OK;
 }
 
+int mocap_locate_objects_dev(mocap_ctx* ctx, const double* obj, const double* err, const int32_t* n_obj, int n_frame_sets,
+                             int max_objects, double* objects, int32_t* drone_index, int32_t* n_objects) {
+    if (!ctx) return MOCAP_EINVAL;
+    if (!obj || !err || !n_obj || !objects || !drone_index || !n_objects || n_frame_sets < 0 || max_objects < 1)
+        return mocap_fail(ctx, MOCAP_EINVAL, "mocap_locate_objects_dev: bad argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+    return launch_locate(ctx, obj, err, n_obj, n_frame_sets, max_objects, objects, drone_index, n_objects);
+}
+
 // ---- S3 on explicit correspondences ----------------------------------------------------------
 int mocap_triangulate_dev(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points,
                           double* X, double* err, uint8_t* valid) {

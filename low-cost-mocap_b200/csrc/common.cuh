@@ -84,6 +84,8 @@ int launch_match(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n, 
 int launch_triangulate(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points,
                        const double* X_in, double* X, double* err, uint8_t* valid);
 int ensure_scratch(mocap_ctx* ctx, size_t bytes);
+int launch_locate(mocap_ctx* ctx, const double* obj, const double* err, const int32_t* n_obj, int n_sets,
+                  int max_objects, double* out, int32_t* drone_index, int32_t* n_out);
 int launch_blob_fallback(mocap_ctx* ctx, int32_t* blob_xy, int32_t* blob_n, int64_t* blob_mom, int32_t* img_flags);
 int launch_match_list(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n, const uint32_t* set_list, uint32_t* set_count,
                       int n_sets_max, double* obj, double* err, int32_t* n_obj, int32_t* set_flags);

@@ -197,3 +197,25 @@ def perturb_poses(poses, seed: int = 1, rot_sigma: float = 0.03, t_sigma: float 
         dR = Rotation.from_rotvec(rng.normal(0.0, rot_sigma, size=3)).as_matrix()
         out.append({"R": dR @ np.asarray(p["R"]), "t": np.asarray(p["t"]).reshape(3) + rng.normal(0.0, t_sigma, size=3)})
     return out
+
+
+def make_drone_points(num_drones: int, num_clutter: int, seed: int = 0, jitter: float = 0.004):
+    """3D point sets for locate_objects (helpers.py:424-480): per drone two markers 0.15 apart and a
+    third 0.095 from both, random pose in a 2 m box, Gaussian jitter, plus clutter points; shuffled.
+    Returns (points [K,3], errors [K])."""
+    rng = np.random.default_rng(seed)
+    pts = []
+    half = 0.075
+    h = np.sqrt(0.095 ** 2 - half ** 2)
+    for _ in range(num_drones):
+        centre = rng.uniform(-1.0, 1.0, size=3)
+        yaw = rng.uniform(-np.pi, np.pi)
+        side = rng.choice([-1.0, 1.0])
+        c, s_ = np.cos(yaw), np.sin(yaw)
+        local = np.array([[half, 0, 0], [-half, 0, 0], [0, side * h, 0]])
+        Rz = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1]])
+        pts.extend(list(local @ Rz.T + centre + rng.normal(0, jitter, size=(3, 3))))
+    pts.extend(list(rng.uniform(-1.0, 1.0, size=(num_clutter, 3))))
+    pts = np.array(pts)
+    order = rng.permutation(len(pts))
+    return pts[order], rng.uniform(0.05, 2.0, size=len(pts))

@@ -23,6 +23,7 @@ Stage map (reference file:line):
   S3 triangulate_one/_many     helpers.py:293-336   triangulate_point(s)
      reprojection_error(s)     helpers.py:203-241   calculate_reprojection_error(s)
   S4 bundle_adjust             helpers.py:244-290   bundle_adjustment
+     locate_objects            helpers.py:424-480   locate_objects (tracking hand-off)
 """
 from __future__ import annotations
 
@@ -179,6 +180,44 @@ class RefPort:
             errors.append(errs[best])
             chosen.append(root_groups[best])
         return np.array(errors), np.array(points), chosen
+
+    # ------------------------------------------------------- tracking hand-off
+    @staticmethod
+    def locate_objects(object_points, errors):
+        """helpers.py:424-480: marker triplets -> [{pos, heading, error, droneIndex}]."""
+        pts = np.asarray(object_points, dtype=np.float64)
+        n = pts.shape[0]
+        dist = np.zeros((n, n))
+        for i in range(n):
+            for j in range(n):
+                dist[i, j] = np.sqrt(np.sum((pts[i] - pts[j]) ** 2))
+        used, found = [], []
+        for i in range(n):
+            if i in used:
+                continue
+            near = np.where(np.abs(dist[i] - 0.095) < 0.025)[0]
+            if len(near) < 2:
+                continue
+            for a in near:
+                hit = False
+                for b in near:
+                    if np.abs(np.sqrt(np.sum((pts[a] - pts[b]) ** 2)) - 0.15) > 0.025:
+                        continue
+                    used += [i, a, b]
+                    centre = (pts[a] + pts[b]) / 2
+                    axis = pts[a] - pts[b]
+                    axis /= linalg.norm(axis)
+                    heading = np.arctan2(axis[1], axis[0])
+                    heading = heading - np.pi if heading > np.pi / 2 else heading
+                    heading = heading + np.pi if heading < -np.pi / 2 else heading
+                    found.append({"pos": centre, "heading": -heading,
+                                  "error": np.mean([errors[i], errors[a], errors[b]]),
+                                  "droneIndex": 0 if (pts[i] - centre)[1] > 0 else 1})
+                    hit = True
+                    break
+                if hit:
+                    break
+        return found
 
     # ------------------------------------------------------------------ S4
     @staticmethod

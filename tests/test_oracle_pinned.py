@@ -99,3 +99,19 @@ def test_ba_residuals_equal_live_reference(synth):
     # poses -> rotvec -> matrix round trip in the port: equal to float32 resolution
     assert r.dtype == np.float32 and r.shape == r_ref.shape
     assert np.allclose(r, r_ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree only exists in the build container")
+def test_locate_objects_equals_live_reference(synth):
+    helpers, _ = ref_harness.load_reference(2)
+    total = 0
+    for seed in range(30):
+        pts, errs = synth.make_drone_points(1 + seed % 3, seed % 5, seed=seed)
+        ref = helpers.locate_objects(pts.copy(), errs.copy())
+        mine = RefPort.locate_objects(pts.copy(), errs.copy())
+        assert len(ref) == len(mine)
+        total += len(ref)
+        for a, b in zip(ref, mine):
+            assert np.array_equal(a["pos"], b["pos"]) and a["heading"] == b["heading"]
+            assert a["error"] == b["error"] and a["droneIndex"] == b["droneIndex"]
+    assert total >= 30

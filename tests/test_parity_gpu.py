@@ -497,3 +497,37 @@ def test_fused_and_split_pipelines_agree(torch, monkeypatch):
     for s in (0, 3, 4, 7):
         k = int(z["nroot"][s])
         assert a["n"][s] == k and np.abs(a["obj"][s, :k] - z["obj"][s, :k]).max() <= X_TOL
+
+
+def test_locate_objects_vs_oracle(torch):
+    """marker triplets -> drone records, batched on the GPU, against the oracle port
+    (pinned to the live reference in tests/test_oracle_pinned.py)."""
+    from oracle.ref_port import RefPort
+    ctx = _ctx(2, max_roots=32)
+    B, R, MO = 60, 32, 6
+    obj = np.zeros((B, R, 3)); err = np.zeros((B, R)); n = np.zeros((B,), np.int32)
+    scenes = []
+    for b in range(B):
+        pts, errs = synth.make_drone_points(b % 4, b % 7, seed=100 + b)
+        if b == 7:
+            pts, errs = pts[:0], errs[:0]                      # empty frame-set
+        scenes.append((pts, errs))
+        n[b] = len(pts); obj[b, :len(pts)] = pts; err[b, :len(pts)] = errs
+    d = ctx.locate_objects(torch.from_numpy(obj).cuda(), torch.from_numpy(err).cuda(), torch.from_numpy(n).cuda(), max_objects=MO)
+    cnt = d["n"].cpu().numpy(); rec = d["objects"].cpu().numpy(); di = d["drone_index"].cpu().numpy()
+    total = 0
+    for b, (pts, errs) in enumerate(scenes):
+        ref = RefPort.locate_objects(pts, errs) if len(pts) else []
+        assert cnt[b] == len(ref), b
+        total += len(ref)
+        for k, o in enumerate(ref):
+            assert np.abs(rec[b, k, :3] - o["pos"]).max() < 1e-12
+            assert abs(rec[b, k, 3] - o["heading"]) < 1e-12 and abs(rec[b, k, 4] - o["error"]) < 1e-12
+            assert di[b, k] == o["droneIndex"]
+    assert total > 60
+    s = pkg.MocapSession([np.eye(3)] * 2)
+    pts, errs = synth.make_drone_points(2, 3, seed=5)
+    got = pkg.locate_objects(pts, errs, session=s)
+    ref = RefPort.locate_objects(pts, errs)
+    assert len(got) == len(ref) == 2 and all(g["droneIndex"] == r["droneIndex"] for g, r in zip(got, ref))
+    assert pkg.locate_objects(np.zeros((0, 3)), np.zeros(0), session=s) == []

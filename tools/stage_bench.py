@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Secondary (not HBM-bound) figures of SURVEY.md §8(d): per-stage throughput on the shapes of
+BASELINE configs 3 and 5.  Prints one JSON object; run on the GPU box:
+
+    python tools/stage_bench.py > gpurun_out/stage_bench.json
+"""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+pkg = importlib.import_module("low-cost-mocap_b200")
+synth = pkg.synth
+from oracle.ref_port import RefPort  # noqa: E402  (CPU baseline leg only)
+
+
+def timed(fn, reps=5):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fn()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def config3_pipeline():
+    C, M, P, B = 8, 16, 64, 4000
+    frames, truth, poses, K = synth.make_frame_pool(C, M, P, seed=1)
+    ctx = pkg.MocapContext(C, 640, 480, max_roots=64)
+    ctx.set_cameras([K] * C, poses)
+    pool = torch.from_numpy(frames).cuda()
+    batch = pool[torch.arange(B, device="cuda") % P].contiguous()     # 9.8 GB
+    out = ctx.alloc_tracks(B)
+    ms = timed(lambda: ctx.pipeline(batch, out=out))
+    n = out["n"].cpu().numpy()
+    flags = out["flags"].cpu().numpy()
+    # CPU reference on a few frame-sets
+    port = RefPort([K] * C)
+    t0 = time.perf_counter()
+    for b in range(3):
+        pts = [port.find_dot(np.repeat(frames[b, c][:, :, None], 3, axis=2)) for c in range(C)]
+        port.match_and_triangulate(pts, poses)
+    cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+    return {"workload": "8 cameras, 16 markers, 4000 frame-sets of 640x480 (9.8 GB resident)", "ms_per_batch": ms,
+            "frame_sets_per_s": B / ms * 1e3, "hbm_gbs": B * C * 307200 / ms / 1e6, "points_per_frame_set": float(n.mean()),
+            "overflow_flags": int((flags != 0).sum()), "cpu_reference_ms_per_frame_set_1core": cpu_ms,
+            "pipeline": os.environ.get("MOCAP_PIPELINE", "fused")}
+
+
+def dlt_rate():
+    C, F = 8, 1_000_000
+    obs_obj, poses, K, pts = synth.make_tracks(C, 2000, seed=3)
+    obs = np.array([[[-1 if v is None else v for v in cam] for cam in fr] for fr in obs_obj], dtype=np.float64)
+    mask = np.array([[cam[0] is not None for cam in fr] for fr in obs_obj], dtype=np.uint8)
+    ctx = pkg.MocapContext(C)
+    ctx.set_cameras([K] * C, poses)
+    reps = F // len(obs)
+    d_obs = torch.from_numpy(np.tile(obs, (reps, 1, 1))).cuda()
+    d_mask = torch.from_numpy(np.tile(mask, (reps, 1))).cuda()
+    X = torch.empty((F, 3), dtype=torch.float64, device="cuda")
+    err = torch.empty((F,), dtype=torch.float64, device="cuda")
+    valid = torch.empty((F,), dtype=torch.uint8, device="cuda")
+    import ctypes as Ct
+    p = lambda t: Ct.c_void_p(t.data_ptr())
+    ctx.use_current_stream()
+    fn = lambda: ctx._check(ctx.lib.mocap_triangulate_dev(ctx.h, p(d_obs), p(d_mask), F, p(X), p(err), p(valid)))
+    ms = timed(fn)
+    return {"workload": "1e6 points x 8 views, DLT + reprojection error", "ms": ms, "dlt_solves_per_s": F / ms * 1e3}
+
+
+def ba_case(C, F, label, cpu_eval=True):
+    obs_obj, poses, K, pts = synth.make_tracks(C, F, seed=9, missing_frac=0.1)
+    start = synth.perturb_poses(poses, seed=10)
+    obs = np.array([[[-1 if v is None else v for v in cam] for cam in fr] for fr in obs_obj], dtype=np.float64)
+    mask = np.array([[cam[0] is not None for cam in fr] for fr in obs_obj], dtype=np.uint8)
+    ctx = pkg.MocapContext(C)
+    ctx.set_cameras([K] * C, start)
+    ctx.bundle_adjust(obs, mask, start)                         # warm-up (allocations)
+    t0 = time.perf_counter()
+    out, rep = ctx.bundle_adjust(obs, mask, start)
+    wall = time.perf_counter() - t0
+    res = {"workload": label, "points": F, "cameras": C, "wall_s": wall, **rep}
+    # residual evaluations per second: one launch evaluates 1 + 6(C-1) residual vectors
+    r0 = time.perf_counter()
+    for _ in range(20):
+        ctx.ba_residuals(obs, mask, start)
+    res["single_residual_vector_ms_incl_copies"] = (time.perf_counter() - r0) / 20 * 1e3
+    if cpu_eval:
+        port = RefPort([K] * C)
+        sub = obs_obj[: min(F, 200)]
+        t0 = time.perf_counter()
+        port.ba_residuals(port.poses_to_params(start), sub)
+        per_point = (time.perf_counter() - t0) / len(sub)
+        n_params = 1 + 7 * (C - 1)
+        res["cpu_reference_s_per_residual_vector_1core"] = per_point * F
+        res["cpu_reference_s_per_jacobian_1core"] = per_point * F * (n_params + 1)
+    return res
+
+
+if __name__ == "__main__":
+    out = {"config3_pipeline": config3_pipeline(), "dlt": dlt_rate(),
+           "ba_config3_batch": ba_case(8, 16000, "config 3 per-batch BA: 8 cameras, 1000 frames x 16 markers = 16000 tracked points"),
+           "ba_config5": ba_case(16, 6400, "config 5 cold start: 16 cameras, 64 markers x 100 frames = 6400 tracked points")}
+    print(json.dumps(out, indent=1))
