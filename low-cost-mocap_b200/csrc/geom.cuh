@@ -150,9 +150,68 @@ GEOM_HD void sym4_null_vector(const Sym4& B, double out[4]) {
         out[r] = best == 0 ? v[r][0] : best == 1 ? v[r][1] : best == 2 ? v[r][2] : v[r][3];
 }
 
+// Fast path for the same null vector: inverse iteration on the LDL^T factors of B.  B = A^T A has one
+// eigenvalue far below the rest whenever the views agree on a point, so y <- B^-1 y converges to the
+// wanted eigenvector at the rate lambda4/lambda3 per step (typically 1e-3 .. 1e-6); rounding errors of
+// the ill-conditioned solves fall along that very eigenvector and are harmless.  Returns false -- and the
+// caller falls back to the Jacobi solver above -- when B is not numerically positive definite in its
+// leading 3x3 block or the iteration has not settled (near-degenerate geometry, lambda3 ~ lambda4).
+// ~25x fewer instructions than the Jacobi sweeps; the two agree to ~1e-13 relative.
+GEOM_HD bool sym4_null_vector_invit(const Sym4& B, double out[4]) {
+    const double b00 = B.v[0], b01 = B.v[1], b02 = B.v[2], b03 = B.v[3], b11 = B.v[4], b12 = B.v[5], b13 = B.v[6];
+    const double b22 = B.v[7], b23 = B.v[8], b33 = B.v[9];
+    if (!(b00 > 0.0)) return false;
+    const double i0 = 1.0 / b00;
+    const double l10 = b01 * i0, l20 = b02 * i0, l30 = b03 * i0;
+    const double d1 = b11 - l10 * b01;
+    if (!(d1 > 1e-14 * b11)) return false;
+    const double i1 = 1.0 / d1;
+    const double l21 = (b12 - l20 * b01) * i1, l31 = (b13 - l30 * b01) * i1;
+    const double d2 = b22 - l20 * b02 - l21 * (l21 * d1);
+    if (!(d2 > 1e-14 * b22)) return false;
+    const double i2 = 1.0 / d2;
+    const double l32 = (b23 - l30 * b02 - l31 * (l21 * d1)) * i2;
+    double d3 = b33 - l30 * b03 - l31 * (l31 * d1) - l32 * (l32 * d2);
+    if (!(d3 == d3)) return false;
+    if (fabs(d3) < 1e-290) d3 = 1e-290;                 // exactly singular data: any huge amplification will do
+    const double i3 = 1.0 / d3;
+    double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 1.0;
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 1.0;
+    bool settled = false;
+    for (int it = 0; it < 40; ++it) {
+        // L z = y ; z /= d ; L^T y' = z
+        const double z0 = y0, z1 = y1 - l10 * z0, z2 = y2 - l20 * z0 - l21 * z1, z3 = y3 - l30 * z0 - l31 * z1 - l32 * z2;
+        const double w3 = z3 * i3;
+        const double w2 = z2 * i2 - l32 * w3;
+        const double w1 = z1 * i1 - l21 * w2 - l31 * w3;
+        const double w0 = z0 * i0 - l10 * w1 - l20 * w2 - l30 * w3;
+        // renormalise by an exact power of two (keeps the iterates in range without rounding)
+        const double m = fmax(fmax(fabs(w0), fabs(w1)), fmax(fabs(w2), fabs(w3)));
+        if (!(m > 0.0) || !(m < 1e300)) return false;
+        int e;
+        (void)frexp(m, &e);
+        y0 = ldexp(w0, -e); y1 = ldexp(w1, -e); y2 = ldexp(w2, -e); y3 = ldexp(w3, -e);
+        if (it >= 2) {
+            // direction change since the previous iterate, sign-insensitive: |y x p| components vs |y||p|
+            const double dot = y0 * p0 + y1 * p1 + y2 * p2 + y3 * p3;
+            const double sg = dot < 0.0 ? -1.0 : 1.0;
+            const double pm = fmax(fmax(fabs(p0), fabs(p1)), fmax(fabs(p2), fabs(p3)));   // both in [0.5, 1)
+            const double ym = fmax(fmax(fabs(y0), fabs(y1)), fmax(fabs(y2), fabs(y3)));
+            const double sc = ym / pm;                   // y ~ sc * sg * p when settled
+            const double dev = fmax(fmax(fabs(y0 - sg * sc * p0), fabs(y1 - sg * sc * p1)),
+                                    fmax(fabs(y2 - sg * sc * p2), fabs(y3 - sg * sc * p3)));
+            if (dev <= 2e-14 * ym) { settled = true; break; }
+        }
+        p0 = y0; p1 = y1; p2 = y2; p3 = y3;
+    }
+    if (!settled) return false;
+    out[0] = y0; out[1] = y1; out[2] = y2; out[3] = y3;
+    return true;
+}
+
 GEOM_HD void dlt_solve(const Sym4& B, double X[3]) {
     double n[4];
-    sym4_null_vector(B, n);
+    if (!sym4_null_vector_invit(B, n)) sym4_null_vector(B, n);
     X[0] = n[0] / n[3]; X[1] = n[1] / n[3]; X[2] = n[2] / n[3];     // helpers.py:321
 }
 

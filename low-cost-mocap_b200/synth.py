@@ -216,6 +216,6 @@ def make_drone_points(num_drones: int, num_clutter: int, seed: int = 0, jitter: 
         Rz = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1]])
         pts.extend(list(local @ Rz.T + centre + rng.normal(0, jitter, size=(3, 3))))
     pts.extend(list(rng.uniform(-1.0, 1.0, size=(num_clutter, 3))))
-    pts = np.array(pts)
+    pts = np.array(pts, dtype=np.float64).reshape(-1, 3)
     order = rng.permutation(len(pts))
     return pts[order], rng.uniform(0.05, 2.0, size=len(pts))

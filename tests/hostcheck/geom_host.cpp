@@ -37,3 +37,21 @@ void hc_triangulate(const double* obs, const uint8_t* mask, int n, int C, const 
     }
 }
 }
+
+// how often the fast null-vector path settles, and how far it is from the Jacobi result
+extern "C" void hc_null_vector_compare(const double* Bs, int n, double* max_rel_diff, int* n_fallback) {
+    double worst = 0.0; int fb = 0;
+    for (int i = 0; i < n; ++i) {
+        Sym4 B; for (int k = 0; k < 10; ++k) B.v[k] = Bs[10 * i + k];
+        double a[4], b[4];
+        sym4_null_vector(B, a);
+        if (!sym4_null_vector_invit(B, b)) { ++fb; continue; }
+        // compare dehomogenised
+        for (int k = 0; k < 3; ++k) {
+            const double xa = a[k] / a[3], xb = b[k] / b[3];
+            const double d = fabs(xa - xb) / fmax(1.0, fabs(xa));
+            if (d > worst) worst = d;
+        }
+    }
+    *max_rel_diff = worst; *n_fallback = fb;
+}
