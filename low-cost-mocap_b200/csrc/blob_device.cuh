@@ -398,7 +398,7 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
     return true;
 }
 
-#define BLOB_WE   128     // segments (and runs) a warp handles
+#define BLOB_WE   256     // segments (and runs) a warp handles
 #define BLOB_WACC 64      // blobs a warp accumulates
 struct WarpSlab {
     unsigned long long acc[BLOB_WACC * 4];
