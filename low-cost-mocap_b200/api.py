@@ -145,6 +145,23 @@ class MocapContext:
             out["chosen"] = chosen
         return out
 
+    def tracks_to_observations(self, xy, n_obj, chosen):
+        """Matcher output -> explicit correspondences for S4 (BASELINE config 3: bundle adjustment on the
+        tracks of a batch).  xy int32 [B*C, max_blobs, 2] (detect), n_obj int32 [B], chosen int32
+        [B, max_roots, C] (match_triangulate(want_chosen=True)).  Returns host arrays obs f64 [P, C, 2],
+        mask uint8 [P, C] with one row per triangulated point, in frame order."""
+        torch = _torch()
+        B, R, Cn = chosen.shape
+        MB = xy.shape[1]
+        keep = torch.arange(R, device=chosen.device)[None, :] < n_obj[:, None].to(torch.int64)      # [B, R]
+        ch = chosen[keep].to(torch.int64)                                                          # [P, C]
+        set_idx = torch.arange(B, device=chosen.device)[:, None].expand(B, R)[keep]                # [P]
+        img = set_idx[:, None] * Cn + torch.arange(Cn, device=chosen.device)[None, :]              # [P, C]
+        mask = ch >= 0
+        pts = xy.view(-1, MB, 2)[img, ch.clamp(min=0)]                                             # [P, C, 2]
+        obs = torch.where(mask[:, :, None], pts.to(torch.float64), torch.zeros((), dtype=torch.float64, device=pts.device))
+        return obs.cpu().numpy(), mask.to(torch.uint8).cpu().numpy()
+
     def alloc_tracks(self, n_sets, device=None):
         torch = _torch()
         dev = device or self.torch_device

@@ -531,3 +531,28 @@ def test_locate_objects_vs_oracle(torch):
     ref = RefPort.locate_objects(pts, errs)
     assert len(got) == len(ref) == 2 and all(g["droneIndex"] == r["droneIndex"] for g, r in zip(got, ref))
     assert pkg.locate_objects(np.zeros((0, 3)), np.zeros(0), session=s) == []
+
+
+def test_config3_shape_pipeline_then_batch_ba(torch):
+    """BASELINE config 3 shape (8 cameras, 16 markers; 150 frame-sets here): S1 -> S2+S3 with the
+    selected correspondences -> S4 on the batch's tracks from perturbed poses.  The adjusted rig must
+    explain the tracks at least as well as the true rig does, under the reference's own objective."""
+    C, M, B = 8, 16, 150
+    frames, truth, poses, K = synth.make_frame_pool(C, M, B, seed=31)
+    ctx = _ctx(C, max_roots=64)
+    ctx.set_cameras([K] * C, poses)
+    d = ctx.detect(torch.from_numpy(frames).cuda())
+    m = ctx.match_triangulate(d["xy"], d["n"], want_chosen=True)
+    assert (m["flags"].cpu().numpy() == 0).all() and (d["flags"].cpu().numpy() == 0).all()
+    obs, mask = ctx.tracks_to_observations(d["xy"], m["n"], m["chosen"])
+    P = int(m["n"].sum())
+    assert obs.shape == (P, C, 2) and mask.shape == (P, C) and (mask.sum(1) >= 2).all()
+    # the observations really are the blobs the matcher chose: re-triangulating them gives the same points
+    X, _, valid = ctx.triangulate(obs, mask)
+    Xm = np.concatenate([m["obj"][b, :int(m["n"][b])].cpu().numpy() for b in range(B)])
+    assert valid.all() and np.abs(X - Xm).max() < 1e-9
+    start = synth.perturb_poses(poses, seed=32)
+    ctx.set_cameras([K] * C, start)
+    out, rep = ctx.bundle_adjust(obs, mask, start)
+    true_cost = 0.5 * np.sum(np.log1p(ctx.ba_residuals(obs, mask, poses).astype(np.float64) ** 2))
+    assert rep["cost_final"] <= true_cost * 1.05 + 1e-6 and rep["cost_final"] < 1e-2 * rep["cost_initial"]
