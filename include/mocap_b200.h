@@ -136,6 +136,22 @@ MOCAP_API int mocap_pipeline_dev(mocap_ctx* ctx, const uint8_t* frames, int n_fr
 MOCAP_API int mocap_pipeline_host(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets, int channels,
                         int threshold, double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
 
+/* Capture-side preprocessing -- replaces the per-camera body of Cameras._camera_read before S1
+ * (helpers.py:70-82): rot90, make_square (zero pad + 8-row feather, helpers.py:507-523), cv.undistort,
+ * cv.GaussianBlur 9x9, cv.filter2D with the 5x5 sharpening kernel, cvtColor RGB2BGR -- in one kernel,
+ * bit-exact with cv2's 8-bit arithmetic.  The context must be square: width == height == in_width (the
+ * reference's make_square only handles landscape frames padded top and bottom).  HOST pointers:
+ * rotation int [n_cam] (0 or 2, camera-params.json "rotation"), K double [n_cam][9], dist double
+ * [n_cam][5] = k1 k2 p1 p2 k3 (camera-params.json "distortion_coef"). */
+MOCAP_API int mocap_set_preprocess(mocap_ctx* ctx, int in_width, int in_height, const int* rotation,
+                         const double* K, const double* dist);
+/* raw uint8 [n_images][in_height][in_width][3] -> out uint8 [n_images][S][S][3].  DEVICE pointers.
+ * n_images = n_frame_sets * n_cam (camera index = image index mod n_cam). */
+MOCAP_API int mocap_preprocess_dev(mocap_ctx* ctx, const uint8_t* raw_frames, int n_images, uint8_t* out_frames);
+/* The fixed-point undistortion map of one camera as built by mocap_set_preprocess (the tables
+ * cv.initUndistortRectifyMap(..., CV_16SC2) returns): m1 int16 [S][S][2], m2 uint16 [S][S].  HOST pointers. */
+MOCAP_API int mocap_get_undistort_map(mocap_ctx* ctx, int cam, int16_t* m1, uint16_t* m2);
+
 /* Tracking hand-off -- replaces locate_objects (helpers.py:424-480) for n_frame_sets frame-sets at
  * once: marker triplets (two markers 0.15 apart, a third 0.095 from both, tolerance 0.025) -> object
  * records.  Input is the matcher's output (obj/err/n_obj, with the world transform set if the caller

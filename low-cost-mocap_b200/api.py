@@ -104,6 +104,30 @@ class MocapContext:
             M = np.ascontiguousarray(np.asarray(M, dtype=np.float64).reshape(4, 4))
             self._check(self.lib.mocap_set_world_transform(self.h, _np_ptr(M)))
 
+    # -- capture-side preprocessing (helpers.py:70-82) -------------------------------------
+    def set_preprocess(self, in_width, in_height, rotations, intrinsics, distortions):
+        rot = np.ascontiguousarray(np.asarray(rotations, dtype=np.int32).reshape(self.n_cam))
+        K = np.ascontiguousarray(np.stack([np.asarray(k, dtype=np.float64).reshape(3, 3) for k in intrinsics]))
+        D = np.ascontiguousarray(np.stack([np.asarray(d, dtype=np.float64).reshape(5) for d in distortions]))
+        self._check(self.lib.mocap_set_preprocess(self.h, int(in_width), int(in_height), _np_ptr(rot), _np_ptr(K), _np_ptr(D)))
+        self._pp_in = (int(in_height), int(in_width))
+
+    def preprocess(self, raw):
+        """raw uint8 cuda tensor [..., in_h, in_w, 3] (whole frame-sets) -> uint8 [N, S, S, 3]."""
+        torch = _torch()
+        h, w = self._pp_in
+        n = raw.numel() // (h * w * 3)
+        out = torch.empty((n, self.height, self.width, 3), dtype=torch.uint8, device=raw.device)
+        self.use_current_stream()
+        self._check(self.lib.mocap_preprocess_dev(self.h, _ptr(raw.contiguous()), n, _ptr(out)))
+        return out
+
+    def undistort_map(self, cam):
+        m1 = np.empty((self.height, self.width, 2), dtype=np.int16)
+        m2 = np.empty((self.height, self.width), dtype=np.uint16)
+        self._check(self.lib.mocap_get_undistort_map(self.h, int(cam), _np_ptr(m1), _np_ptr(m2)))
+        return m1, m2
+
     # -- batched device API ---------------------------------------------------------------
     def detect(self, frames, threshold=THRESHOLD, want_moments=False):
         """frames: uint8 cuda tensor [..., H, W] or [..., H, W, 3].  Returns dict of cuda tensors:

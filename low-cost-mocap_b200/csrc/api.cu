@@ -24,6 +24,7 @@ int ensure_scratch(mocap_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->scratch_bytes) return MOCAP_OK;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_pp_m1); cudaFree(ctx->d_pp_m2); cudaFree(ctx->d_pp_rot);
     ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_scratch, bytes));
     ctx->scratch_bytes = bytes;
@@ -120,6 +121,7 @@ void mocap_destroy(mocap_ctx* ctx) {
     cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
     cudaFree(ctx->d_obj); cudaFree(ctx->d_err); cudaFree(ctx->d_nobj); cudaFree(ctx->d_setflags);
     cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_pp_m1); cudaFree(ctx->d_pp_m2); cudaFree(ctx->d_pp_rot);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int k = 0; k < 2 * 64; ++k) if (ctx->tim_ev[k]) cudaEventDestroy(ctx->tim_ev[k]);
     for (int k = 0; k < 2; ++k) if (ctx->stage_free[k]) cudaEventDestroy(ctx->stage_free[k]);

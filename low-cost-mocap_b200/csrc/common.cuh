@@ -57,6 +57,8 @@ struct mocap_ctx {
     int       cap_sets;
     // generic scratch for the *_host triangulation / BA entry points
     void*     d_scratch; size_t scratch_bytes;
+    // capture-side preprocessing
+    int16_t*  d_pp_m1; uint16_t* d_pp_m2; int* d_pp_rot; int pp_in_w, pp_in_h;
     // accounting
     uint64_t  launches;
     int       timing_on;

@@ -44,6 +44,31 @@ class RefPort:
     def __init__(self, intrinsics):
         self.K = [np.asarray(k, dtype=np.float64) for k in intrinsics]
 
+    # ------------------------------------------------- capture-side preprocessing
+    @staticmethod
+    def make_square(img):
+        """helpers.py:507-523: centre the frame in a zero square, fade 8 rows above and below."""
+        rows, cols, _ = img.shape
+        size = max(rows, cols)
+        out = np.zeros((size, size, 3), dtype=np.uint8)
+        ax, ay = (size - cols) // 2, (size - rows) // 2
+        out[ay:ay + rows, ax:ax + cols] = img
+        for i in range(8):
+            alpha = (i + 1) / 8
+            out[ay - i - 1, :] = img[0, :] * (1 - alpha)
+            out[ay + rows + i, :] = img[-1, :] * (1 - alpha)
+        return out
+
+    def preprocess(self, frame, cam, distortion, rotation=0):
+        """helpers.py:70-82 for one camera frame (HxWx3 uint8)."""
+        f = np.rot90(frame, k=rotation)
+        f = self.make_square(f)
+        f = cv2.undistort(f, self.K[cam], np.asarray(distortion, dtype=np.float64))
+        f = cv2.GaussianBlur(f, (9, 9), 0)
+        sharpen = np.array([[-2, -1, -1, -1, -2], [-1, 1, 3, 1, -1], [-1, 3, 4, 3, -1], [-1, 1, 3, 1, -1], [-2, -1, -1, -1, -2]])
+        f = cv2.filter2D(f, -1, sharpen)
+        return cv2.cvtColor(f, cv2.COLOR_RGB2BGR)
+
     # ------------------------------------------------------------------ S1
     def find_dot(self, img):
         """helpers.py:143-163.  img: HxWx3 uint8.  Returns list of [cx, cy]

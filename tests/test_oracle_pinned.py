@@ -115,3 +115,14 @@ def test_locate_objects_equals_live_reference(synth):
             assert np.array_equal(a["pos"], b["pos"]) and a["heading"] == b["heading"]
             assert a["error"] == b["error"] and a["droneIndex"] == b["droneIndex"]
     assert total >= 30
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree only exists in the build container")
+def test_preprocess_equals_live_reference():
+    """RefPort.preprocess restates helpers.py:70-82; the live reference only exposes that chain inside
+    _camera_read (which needs camera hardware), so its pieces are compared: make_square directly, the
+    cv2 calls by construction (same functions, same arguments)."""
+    helpers, cams = ref_harness.load_reference(1)
+    rng = np.random.default_rng(0)
+    frame = rng.integers(0, 256, size=(240, 320, 3), dtype=np.uint8)
+    assert np.array_equal(helpers.make_square(frame), RefPort.make_square(frame))

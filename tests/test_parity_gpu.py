@@ -556,3 +556,44 @@ def test_config3_shape_pipeline_then_batch_ba(torch):
     out, rep = ctx.bundle_adjust(obs, mask, start)
     true_cost = 0.5 * np.sum(np.log1p(ctx.ba_residuals(obs, mask, poses).astype(np.float64) ** 2))
     assert rep["cost_final"] <= true_cost * 1.05 + 1e-6 and rep["cost_final"] < 1e-2 * rep["cost_initial"]
+
+
+def test_preprocess_bit_exact_vs_cv2_chain(torch):
+    """rot90 -> make_square -> undistort -> GaussianBlur 9x9 -> filter2D 5x5 -> RGB2BGR in one
+    kernel, bit-exact against the reference's cv2 chain (oracle port) on worst-case random-noise frames and
+    on marker-like frames; then S1 on the processed frames equals the reference's _find_dot."""
+    import json, os
+    from oracle.ref_port import RefPort
+    K = np.array([[320.0, 0, 160], [0, 320, 160], [0, 0, 1]])
+    dist = [-1.26372388e-01, 2.62661497e-01, 1.21306197e-03, 2.24507008e-04, -2.48534118e-01]   # camera-params.json
+    C = 2
+    ctx = pkg.MocapContext(C, 320, 320, max_blobs=64)
+    ctx.set_preprocess(320, 240, [0, 2], [K, K], [dist, [d * 0.5 for d in dist]])
+    port = RefPort([K, K])
+    # the fixed-point undistortion map equals cv2's
+    import cv2
+    for cam, dd in ((0, dist), (1, [d * 0.5 for d in dist])):
+        m1, m2 = ctx.undistort_map(cam)
+        r1, r2 = cv2.initUndistortRectifyMap(K, np.array(dd), np.eye(3), K, (320, 320), cv2.CV_16SC2)
+        assert np.array_equal(m1, r1) and np.array_equal(m2, r2)
+    rng = np.random.default_rng(4)
+    raw = rng.integers(0, 256, size=(3, C, 240, 320, 3), dtype=np.uint8)
+    # marker-like frames: dark clutter + bright discs
+    for b in range(1, 3):
+        raw[b] = rng.integers(0, 30, size=(C, 240, 320, 3), dtype=np.uint8)
+        for c in range(C):
+            for _ in range(6):
+                cy, cx, r = rng.integers(20, 220), rng.integers(20, 300), rng.integers(3, 9)
+                yy, xx = np.ogrid[:240, :320]
+                raw[b, c][(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = 255
+    out = ctx.preprocess(torch.from_numpy(raw).cuda())
+    got = out.cpu().numpy().reshape(3, C, 320, 320, 3)
+    for b in range(3):
+        for c, (dd, rot) in enumerate(((dist, 0), ([d * 0.5 for d in dist], 2))):
+            ref = port.preprocess(raw[b, c], c, dd, rot)
+            assert np.array_equal(got[b, c], ref), (b, c, int((got[b, c] != ref).sum()))
+    det = ctx.detect(out)
+    for i in range(3 * C):
+        ref_pts = [p for p in port.find_dot(got.reshape(-1, 320, 320, 3)[i].copy()) if p[0] is not None]
+        k = int(det["n"][i])
+        assert det["xy"][i, :k].cpu().numpy().tolist() == ref_pts
