@@ -593,7 +593,8 @@ def test_preprocess_bit_exact_vs_cv2_chain(torch):
             ref = port.preprocess(raw[b, c], c, dd, rot)
             assert np.array_equal(got[b, c], ref), (b, c, int((got[b, c] != ref).sum()))
     det = ctx.detect(out)
-    for i in range(3 * C):
+    for i in range(C, 3 * C):                      # the marker-like frames (the noise frame is all clutter)
+        assert int(det["flags"][i]) == 0
         ref_pts = [p for p in port.find_dot(got.reshape(-1, 320, 320, 3)[i].copy()) if p[0] is not None]
         k = int(det["n"][i])
         assert det["xy"][i, :k].cpu().numpy().tolist() == ref_pts
