@@ -578,14 +578,16 @@ def test_preprocess_bit_exact_vs_cv2_chain(torch):
         assert np.array_equal(m1, r1) and np.array_equal(m2, r2)
     rng = np.random.default_rng(4)
     raw = rng.integers(0, 256, size=(3, C, 240, 320, 3), dtype=np.uint8)
-    # marker-like frames: dark clutter + bright discs
+    # marker-like frames: dark clutter + bright Gaussian spots (stay solid through blur + sharpen;
+    # hard-edged discs turn into rings, i.e. blobs with holes, which are outside the S1 contract)
+    yy, xx = np.mgrid[:240, :320]
     for b in range(1, 3):
         raw[b] = rng.integers(0, 30, size=(C, 240, 320, 3), dtype=np.uint8)
         for c in range(C):
             for _ in range(6):
-                cy, cx, r = rng.integers(20, 220), rng.integers(20, 300), rng.integers(3, 9)
-                yy, xx = np.ogrid[:240, :320]
-                raw[b, c][(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = 255
+                cy, cx, sg = rng.uniform(20, 220), rng.uniform(20, 300), rng.uniform(1.5, 4.0)
+                spot = (255 * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * sg * sg))).astype(np.uint8)
+                raw[b, c] = np.maximum(raw[b, c], spot[:, :, None])
     out = ctx.preprocess(torch.from_numpy(raw).cuda())
     got = out.cpu().numpy().reshape(3, C, 320, 320, 3)
     for b in range(3):
