@@ -213,14 +213,15 @@ def run_gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    # clocks / throttle reasons are sampled from the warm-up through the end of the timed region
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(3, args.warmup)):
         step()
     sync_all()
 
     # ---- timed region: resident inputs -----------------------------------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ctx.enable_kernel_timing(True)
     ctx.detect_kernel_ms(reset=True)
     launches0 = ctx.launch_count()
@@ -321,7 +322,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--profile", action="store_true",

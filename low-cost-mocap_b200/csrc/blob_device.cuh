@@ -76,15 +76,6 @@ __device__ __forceinline__ unsigned block_scan_excl(unsigned v, unsigned& total,
     return base + x - v;
 }
 
-__device__ __forceinline__ int seg_find(const uint32_t* seg, int n, uint32_t pos) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if ((seg[mid] >> 16) < pos) lo = mid + 1; else hi = mid;
-    }
-    return (lo < n && (seg[lo] >> 16) == pos) ? lo : -1;
-}
-
 __device__ __forceinline__ unsigned uf_find(volatile unsigned* parent, unsigned x) {
     unsigned p;
     while ((p = parent[x]) != x) x = p;

@@ -108,8 +108,28 @@ def ba_case(C, F, label, cpu_eval=True):
     return res
 
 
+def preprocess_rate():
+    C, B = 4, 2000
+    K = np.array([[320.0, 0, 160], [0, 320, 160], [0, 0, 1]])
+    dist = [-1.26372388e-01, 2.62661497e-01, 1.21306197e-03, 2.24507008e-04, -2.48534118e-01]
+    ctx = pkg.MocapContext(C, 320, 320)
+    ctx.set_preprocess(320, 240, [0] * C, [K] * C, [dist] * C)
+    raw = torch.randint(0, 256, (B, C, 240, 320, 3), dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: ctx.preprocess(raw))
+    port = RefPort([K] * C)
+    frame = raw[0, 0].cpu().numpy()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        port.preprocess(frame, 0, dist, 0)
+    cpu_ms = (time.perf_counter() - t0) / 20 * 1e3
+    n_img = B * C
+    return {"workload": "8000 raw 320x240x3 frames -> 320x320x3 (undistort + Gaussian 9x9 + 5x5 filter), one kernel",
+            "ms": ms, "frames_per_s": n_img / ms * 1e3, "algorithmic_gbs": n_img * (240 * 320 * 3 + 320 * 320 * 3) / ms / 1e6,
+            "cpu_reference_ms_per_frame_1core": cpu_ms}
+
+
 if __name__ == "__main__":
-    out = {"config3_pipeline": config3_pipeline(), "dlt": dlt_rate(),
+    out = {"preprocess": preprocess_rate(),"config3_pipeline": config3_pipeline(), "dlt": dlt_rate(),
            "ba_config3_batch": ba_case(8, 16000, "config 3 per-batch BA: 8 cameras, 1000 frames x 16 markers = 16000 tracked points"),
            "ba_config5": ba_case(16, 6400, "config 5 cold start: 16 cameras, 64 markers x 100 frames = 6400 tracked points")}
     print(json.dumps(out, indent=1))
