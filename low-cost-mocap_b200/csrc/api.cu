@@ -91,6 +91,7 @@ int mocap_create(mocap_ctx** out, const mocap_config* cfg) {
     do {
         if (cudaMalloc(&ctx->d_tables, sizeof(CameraTables)) != cudaSuccess) { st = MOCAP_ENOMEM; break; }
         if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { st = MOCAP_ECUDA; break; }
+        if (cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking) != cudaSuccess) { st = MOCAP_ECUDA; break; }
         for (int k = 0; k < 2 * 64; ++k)
             if (cudaEventCreate(&ctx->tim_ev[k]) != cudaSuccess) { st = MOCAP_ECUDA; break; }
         if (st) break;
@@ -123,6 +124,7 @@ void mocap_destroy(mocap_ctx* ctx) {
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_pp_m1); cudaFree(ctx->d_pp_m2); cudaFree(ctx->d_pp_rot);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
     for (int k = 0; k < 2 * 64; ++k) if (ctx->tim_ev[k]) cudaEventDestroy(ctx->tim_ev[k]);
     for (int k = 0; k < 2; ++k) if (ctx->stage_free[k]) cudaEventDestroy(ctx->stage_free[k]);
     delete ctx;
@@ -329,16 +331,22 @@ int mocap_pipeline_host(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets,
     if (st) return st;
     st = ensure_images(ctx, chunk * C);
     if (st) return st;
-    cudaEvent_t copied;
-    CUDA_TRY(ctx, cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+    cudaEvent_t copied[2];
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&copied[0], cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&copied[1], cudaEventDisableTiming));
+    // the copies must not start before earlier work on the caller's stream has finished with the staging buffers
+    CUDA_TRY(ctx, cudaEventRecord(copied[0], ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, copied[0], 0));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream2, copied[0], 0));
     int k = 0, n_chunks = 0;
     for (int s0 = 0; s0 < n_frame_sets; s0 += chunk, k ^= 1, ++n_chunks) {
         const int ns = (n_frame_sets - s0 < chunk) ? n_frame_sets - s0 : chunk;
-        if (n_chunks >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[k], 0));
+        cudaStream_t cs = k ? ctx->copy_stream2 : ctx->copy_stream;
+        if (n_chunks >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->stage_free[k], 0));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[k], frames + (size_t)s0 * set_bytes, (size_t)ns * set_bytes,
-                                      cudaMemcpyHostToDevice, ctx->copy_stream));
-        CUDA_TRY(ctx, cudaEventRecord(copied, ctx->copy_stream));
-        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, copied, 0));
+                                      cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(ctx, cudaEventRecord(copied[k], cs));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, copied[k], 0));
         if (ctx->use_fused && channels == 1) {
             st = launch_pipeline_fused(ctx, ctx->d_stage[k], ns, threshold, ctx->d_obj + (size_t)s0 * RM * 3, ctx->d_err + (size_t)s0 * RM,
                                        ctx->d_nobj + s0, ctx->d_setflags + s0);
@@ -353,7 +361,9 @@ int mocap_pipeline_host(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets,
                           ctx->d_nobj + s0, ctx->d_setflags + s0, nullptr);
         if (st) break;
     }
-    cudaEventDestroy(copied);
+    cudaEventDestroy(copied[1]);
+    cudaEvent_t copied0 = copied[0];
+    cudaEventDestroy(copied0);
     if (st) return st;
     const size_t n = (size_t)n_frame_sets;
     CUDA_TRY(ctx, cudaMemcpyAsync(obj, ctx->d_obj, n * RM * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

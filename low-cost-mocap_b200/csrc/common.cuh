@@ -30,6 +30,7 @@ struct mocap_ctx {
     mocap_config cfg;
     cudaStream_t stream;
     cudaStream_t copy_stream;
+    cudaStream_t copy_stream2;   // staging buffers alternate between two copy streams (two copy engines in flight)
     char         err[512];
     bool         cameras_set;
     CameraTables* d_tables;
