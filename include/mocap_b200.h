@@ -177,6 +177,18 @@ MOCAP_API int mocap_triangulate_host(mocap_ctx* ctx, const double* obs, const ui
 MOCAP_API int mocap_reprojection_errors_host(mocap_ctx* ctx, const double* obs, const uint8_t* mask,
                                    const double* X, int n_points, double* err, uint8_t* valid);
 
+/* Cold-start extrinsics -- replaces the body of calculate_camera_pose up to its bundle_adjustment call
+ * (index.py:229-270): per adjacent camera pair a fundamental matrix from the common observations,
+ * E = K1^T F K0 (cv.sfm.essentialFromFundamental with the intrinsics of cameras 0 and 1), the four
+ * motions of cv.sfm.motionFromEssential, the reference's cheirality vote and the pose chain.  The
+ * reference's F comes from a randomised cv.findFundamentalMat(FM_RANSAC); here F is a deterministic
+ * normalised 8-point estimate re-fitted twice on its 1 px Sampson inliers, or -- F_given != NULL --
+ * supplied by the caller (double [n_cam-1][9], x2^T F x1 = 0).  HOST pointers: obs/mask as for
+ * mocap_bundle_adjust_host; R [n_cam][9], t [n_cam][3] out; F_used [n_cam-1][9] and votes
+ * [n_cam-1][4] (points in front of the cameras per candidate) may be NULL. */
+MOCAP_API int mocap_calibrate_init_host(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points,
+                              const double* F_given, double* R, double* t, double* F_used, int* votes);
+
 /* S4 -- replaces bundle_adjustment (helpers.py:244-290): robust (Cauchy) trust-region
  * least squares over the poses of cameras 1..C-1 (rotation vector + translation;
  * camera 0 pinned at (I,0); the reference's focal parameters are dead, helpers.py:267-270),

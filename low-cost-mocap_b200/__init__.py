@@ -18,5 +18,6 @@ from .api import (  # noqa: F401
     calculate_reprojection_errors,
     bundle_adjustment,
     locate_objects,
+    calculate_camera_poses,
     install_into,
 )

@@ -58,6 +58,7 @@ SYMBOLS = {
     "mocap_triangulate_dev": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P]),
     "mocap_triangulate_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P]),
     "mocap_reprojection_errors_host": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),
+    "mocap_calibrate_init_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
     "mocap_ba_default_options": (None, [C.POINTER(BAOptions)]),
     "mocap_bundle_adjust_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.POINTER(BAOptions), C.POINTER(BAReport)]),
     "mocap_ba_residuals_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_int)]),

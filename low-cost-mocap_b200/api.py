@@ -260,6 +260,18 @@ class MocapContext:
         self._check(self.lib.mocap_reprojection_errors_host(self.h, _np_ptr(obs), _np_ptr(mask), _np_ptr(X), F, _np_ptr(err), _np_ptr(valid)))
         return err, valid
 
+    def calibrate_init(self, obs, mask, F_given=None):
+        """Chain of relative poses from 2D tracks (index.py:229-270).  Returns (poses, F_used [C-1,3,3], votes [C-1,4])."""
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        Cn = self.n_cam
+        R = np.empty((Cn, 3, 3)); t = np.empty((Cn, 3))
+        Fu = np.empty((Cn - 1, 3, 3)); votes = np.empty((Cn - 1, 4), dtype=np.int32)
+        Fg = None if F_given is None else np.ascontiguousarray(np.asarray(F_given, dtype=np.float64).reshape(Cn - 1, 3, 3))
+        self._check(self.lib.mocap_calibrate_init_host(self.h, _np_ptr(obs), _np_ptr(mask), obs.shape[0], _np_ptr(Fg),
+                                                       _np_ptr(R), _np_ptr(t), _np_ptr(Fu), _np_ptr(votes)))
+        return [{"R": R[i].copy(), "t": t[i].copy()} for i in range(Cn)], Fu, votes
+
     def ba_residuals(self, obs, mask, poses):
         obs = np.ascontiguousarray(obs, dtype=np.float64)
         mask = np.ascontiguousarray(mask, dtype=np.uint8)
@@ -491,6 +503,25 @@ def bundle_adjustment(image_points, camera_poses, socketio, session=None):
     obs, mask = _split_observations(image_points)
     with s._lock:
         out, _ = s.ctx_with_poses(camera_poses).bundle_adjust(obs, mask, camera_poses)
+    if socketio is not None:
+        socketio.emit("camera-pose", {"camera_poses": [{"R": p["R"].tolist(), "t": p["t"].tolist()} for p in out]})
+    return out
+
+
+def calculate_camera_poses(image_points, socketio=None, session=None):
+    """The computation of the reference's ``calculate-camera-pose`` handler (index.py:229-277): cold-start
+    chain of relative poses, then bundle adjustment.  ``image_points`` is the (F, C, 2) list the UI sends
+    (``data["cameraPoints"]``) with ``None`` for missing views.  Returns the list of {"R", "t"}."""
+    s = session or MocapSession.default()
+    obs, mask = _split_observations(image_points)
+    n_cam = obs.shape[1]
+    with s._lock:
+        ctx = s.ctx(n_cam)
+        ident = [{"R": np.eye(3), "t": np.zeros(3)} for _ in range(n_cam)]
+        ctx.set_cameras(s.intrinsics[:n_cam], ident)
+        start, _, _ = ctx.calibrate_init(obs, mask)
+        ctx.set_cameras(s.intrinsics[:n_cam], start)
+        out, _ = ctx.bundle_adjust(obs, mask, start)
     if socketio is not None:
         socketio.emit("camera-pose", {"camera_poses": [{"R": p["R"].tolist(), "t": p["t"].tolist()} for p in out]})
     return out

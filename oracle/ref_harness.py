@@ -90,3 +90,56 @@ class NullSocket:
 
     def emit(self, *a, **k):
         self.count += 1
+
+
+_index_cached = None
+
+
+def load_reference_index(num_cameras: int, intrinsic_matrix=None):
+    """Import the reference's index.py (the Socket.IO handlers) with pass-through stubs for the web /
+    serial / trajectory packages it needs at import time (flask, flask_socketio, flask_cors, serial,
+    ruckig: none installed here, none on the hot path).  Returns (index_module, helpers, cameras)."""
+    global _index_cached
+    helpers, cams = load_reference(num_cameras, intrinsic_matrix)
+    if _index_cached is None:
+        def passthrough_decorator(*a, **k):
+            def deco(fn):
+                return fn
+            return deco
+
+        flask = types.ModuleType("flask")
+
+        class Flask:
+            def __init__(self, *a, **k):
+                pass
+            route = staticmethod(passthrough_decorator)
+
+        flask.Flask = Flask
+        flask.Response = object
+        flask.request = types.SimpleNamespace()
+        fsio = types.ModuleType("flask_socketio")
+
+        class SocketIO:
+            def __init__(self, *a, **k):
+                self.events = []
+            on = staticmethod(passthrough_decorator)
+
+            def emit(self, *a, **k):
+                self.events.append((a, k))
+
+            def run(self, *a, **k):
+                pass
+
+        fsio.SocketIO = SocketIO
+        fcors = types.ModuleType("flask_cors")
+        fcors.CORS = lambda *a, **k: None
+        serial = types.ModuleType("serial")
+        serial.Serial = lambda *a, **k: types.SimpleNamespace(write=lambda *a, **k: None)
+        ruckig = types.ModuleType("ruckig")
+        for name in ("InputParameter", "OutputParameter", "Result", "Ruckig"):
+            setattr(ruckig, name, object)
+        for name, mod in (("flask", flask), ("flask_socketio", fsio), ("flask_cors", fcors), ("serial", serial), ("ruckig", ruckig)):
+            sys.modules.setdefault(name, mod)
+        import index  # the reference module, unmodified
+        _index_cached = index
+    return _index_cached, helpers, cams

@@ -244,6 +244,36 @@ class RefPort:
                     break
         return found
 
+    # --------------------------------------------------- cold-start extrinsics
+    def calibrate_init(self, image_points, rng_seed=0, return_F=False):
+        """index.py:229-270: chain of relative poses from adjacent camera pairs.  cv.findFundamentalMat is
+        randomised; cv2.setRNGSeed makes this restatement repeatable (the reference never seeds it)."""
+        pts = np.array(image_points)
+        by_cam = pts.transpose((1, 0, 2))
+        n_cam = by_cam.shape[0]
+        poses = [{"R": np.eye(3), "t": np.array([[0], [0], [0]], dtype=np.float32)}]
+        Fs = []
+        cv2.setRNGSeed(rng_seed)
+        for c in range(n_cam - 1):
+            a, b = by_cam[c], by_cam[c + 1]
+            both = np.where(np.all(a != None, axis=1) & np.all(b != None, axis=1))[0]      # noqa: E711
+            a = np.take(a, both, axis=0).astype(np.float32)
+            b = np.take(b, both, axis=0).astype(np.float32)
+            F, _ = cv2.findFundamentalMat(a, b, cv2.FM_RANSAC, 1, 0.99999)
+            Fs.append(F)
+            E = sfm_shim.essentialFromFundamental(F, self.K[0], self.K[1])
+            Rs, ts = sfm_shim.motionFromEssential(E)
+            best_R, best_t, best = None, None, 0
+            for i in range(4):
+                X = self.triangulate_many(np.hstack([np.expand_dims(a, axis=1), np.expand_dims(b, axis=1)]),
+                                          [poses[-1], {"R": Rs[i], "t": ts[i]}])
+                Xc = np.array([Rs[i].T @ x for x in X])
+                front = np.sum(X[:, 2] > 0) + np.sum(Xc[:, 2] > 0)
+                if front > best:
+                    best, best_R, best_t = front, Rs[i], ts[i]
+            poses.append({"R": best_R @ poses[-1]["R"], "t": poses[-1]["t"] + (poses[-1]["R"] @ best_t)})
+        return (poses, Fs) if return_F else poses
+
     # ------------------------------------------------------------------ S4
     @staticmethod
     def params_to_poses(params):

@@ -134,3 +134,15 @@ def test_geometry_code_matches_golden_on_host(geom_host, name):
     assert valid.all()
     assert np.abs(X - z["X"]).max() < 1e-9
     assert np.array_equal(err, z["err"])
+
+
+def test_header_is_plain_c_and_example_links(built_lib, tmp_path):
+    """include/mocap_b200.h compiles as C (not C++) and the plain-C example links against the library."""
+    exe = tmp_path / "pipeline_host"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "pipeline_host.c"), "-L", os.path.dirname(built_lib),
+                           "-lmocap_b200", "-Wl,-rpath," + os.path.dirname(built_lib), "-o", str(exe)])
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([str(exe)], capture_output=True, text=True)
+        assert r.returncode == 1 and "no usable CUDA device" in r.stderr      # fails loudly, no CPU fallback

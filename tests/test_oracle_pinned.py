@@ -126,3 +126,31 @@ def test_preprocess_equals_live_reference():
     rng = np.random.default_rng(0)
     frame = rng.integers(0, 256, size=(240, 320, 3), dtype=np.uint8)
     assert np.array_equal(helpers.make_square(frame), RefPort.make_square(frame))
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree only exists in the build container")
+def test_calibrate_init_equals_live_reference(synth):
+    """index.py:229-270 through the real handler: bundle_adjustment is intercepted so that the chain it
+    is handed can be compared with the port's (same cv2 RNG seed on both sides)."""
+    import cv2
+    C = 3
+    index, helpers, cams = ref_harness.load_reference_index(C)
+    obs, poses, K, _ = synth.make_tracks(C, 40, seed=8, missing_frac=0.15)
+    captured = {}
+
+    def fake_ba(image_points, camera_poses, sio):
+        captured["poses"] = [{"R": np.array(p["R"], dtype=np.float64), "t": np.array(p["t"], dtype=np.float64)} for p in camera_poses]
+        return camera_poses
+    real_ba, real_ser = index.bundle_adjustment, index.camera_pose_to_serializable
+    index.bundle_adjustment = fake_ba
+    index.camera_pose_to_serializable = lambda p: p
+    try:
+        cv2.setRNGSeed(0)
+        index.calculate_camera_pose({"cameraPoints": obs.tolist()})
+    finally:
+        index.bundle_adjustment, index.camera_pose_to_serializable = real_ba, real_ser
+    mine = RefPort([K] * C).calibrate_init(obs.tolist(), rng_seed=0)
+    assert len(mine) == len(captured["poses"]) == C
+    for a, b in zip(mine, captured["poses"]):
+        assert np.array_equal(np.asarray(a["R"], dtype=np.float64), b["R"])
+        assert np.array_equal(np.asarray(a["t"], dtype=np.float64).ravel(), b["t"].ravel())

@@ -600,3 +600,71 @@ def test_preprocess_bit_exact_vs_cv2_chain(torch):
         ref_pts = [p for p in port.find_dot(got.reshape(-1, 320, 320, 3)[i].copy()) if p[0] is not None]
         k = int(det["n"][i])
         assert det["xy"][i, :k].cpu().numpy().tolist() == ref_pts
+
+
+def test_calibrate_init_vs_oracle(torch):
+    """SURVEY §8(f) #4.  (i) Given the reference's own fundamental matrices (cv2 RANSAC, seeded) the essential
+    decomposition, cheirality vote and pose chain equal the reference's (index.py:247-265).  (ii) With the
+    deterministic 8-point estimator the chain is at least as close to the truth, and after bundle adjustment
+    the rig explains the tracks as well as the adjusted reference chain does."""
+    from oracle.ref_port import RefPort
+    C = 4
+    obs_obj, poses, K, pts = synth.make_tracks(C, 80, seed=14, missing_frac=0.1)
+    obs = np.array([[[-1 if v is None else v for v in cam] for cam in fr] for fr in obs_obj], dtype=np.float64)
+    mask = np.array([[cam[0] is not None for cam in fr] for fr in obs_obj], dtype=np.uint8)
+    port = RefPort([K] * C)
+    ref_chain, Fs = port.calibrate_init(obs_obj.tolist(), rng_seed=0, return_F=True)
+    ctx = _ctx(C)
+    ctx.set_cameras([K] * C, [{"R": np.eye(3), "t": np.zeros(3)}] * C)
+    chain, F_used, votes = ctx.calibrate_init(obs, mask, F_given=np.stack(Fs))
+    assert np.allclose(F_used, np.stack(Fs))
+    for a, b in zip(chain, ref_chain):                           # (i)
+        assert np.abs(a["R"] - np.asarray(b["R"], dtype=np.float64)).max() < 1e-8
+        assert np.abs(a["t"] - np.asarray(b["t"], dtype=np.float64).ravel()).max() < 1e-8
+    assert (votes.max(axis=1) > 0).all()
+
+    def rot_err_deg(chain_):
+        errs = []
+        for c in range(1, C):
+            Rt, Re = np.asarray(poses[c]["R"]), np.asarray(chain_[c]["R"], dtype=np.float64)
+            errs.append(np.degrees(np.arccos(np.clip((np.trace(Rt.T @ Re) - 1) / 2, -1, 1))))
+        return max(errs)
+    own, F_own, _ = ctx.calibrate_init(obs, mask)                # (ii)
+    assert rot_err_deg(own) <= rot_err_deg(ref_chain) + 0.5
+    for c in range(C - 1):                                       # epipolar constraint holds on the tracks
+        both = (mask[:, c] & mask[:, c + 1]).astype(bool)
+        x1 = np.c_[obs[both, c], np.ones(both.sum())]; x2 = np.c_[obs[both, c + 1], np.ones(both.sum())]
+        l = x1 @ F_own[c].T
+        d = np.abs(np.sum(x2 * l, axis=1)) / np.sqrt(l[:, 0] ** 2 + l[:, 1] ** 2)
+        assert np.median(d) < 1.0
+    s = pkg.MocapSession([K] * C)
+    final = pkg.calculate_camera_poses(obs_obj.tolist(), session=s)
+    ctx.set_cameras([K] * C, final)
+    cost_own = 0.5 * np.sum(np.log1p(ctx.ba_residuals(obs, mask, final).astype(np.float64) ** 2))
+    ref_start = [{"R": np.asarray(p["R"], dtype=np.float64), "t": np.asarray(p["t"], dtype=np.float64).ravel()} for p in ref_chain]
+    ctx.set_cameras([K] * C, ref_start)
+    adj_ref, rep = ctx.bundle_adjust(obs, mask, ref_start)
+    assert cost_own <= rep["cost_final"] * 1.05 + 1e-6
+    ctx.set_cameras([K] * C, final)
+    X, _, valid = ctx.triangulate(obs, mask)
+    A = X - X.mean(0); Bm = pts - pts.mean(0)
+    A *= np.linalg.norm(Bm) / np.linalg.norm(A)
+    U, _, Vt = np.linalg.svd(A.T @ Bm)
+    assert np.abs(A @ (U @ Vt) - Bm).max() < 0.03
+
+
+def test_plain_c_example_runs(torch, tmp_path):
+    """examples/pipeline_host.c (what a cgo / JNI binding would call) through the host entry point."""
+    import os, subprocess
+    from tests.util import ROOT
+    lib_dir = os.path.join(ROOT, "low-cost-mocap_b200")
+    exe = tmp_path / "pipeline_host"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "pipeline_host.c"),
+                           "-L", lib_dir, "-lmocap_b200", "-Wl,-rpath," + lib_dir, "-o", str(exe)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith("frame-set")]
+    assert len(lines) == 4
+    for l in lines:
+        x, y, z = [float(v) for v in l.split(":")[1].split()[:3]]
+        assert abs(x - 0.1) < 0.01 and abs(y - 0.05) < 0.01 and abs(z - 3.0) < 0.05
