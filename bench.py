@@ -274,6 +274,10 @@ def run_gpu_arm(args):
 
     kernel_name = ("k_threshold_segments_c1 (three-kernel pipeline)" if os.environ.get("MOCAP_PIPELINE") == "split"
                    else "k_pipeline_fused (threshold + blob reduce + match/DLT in one pass)")
+    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this
+    # workload (profiles/ncu_full_r01_fused.csv: dram__bytes_read.sum 12.307234 GB + dram__bytes_write.sum
+    # 28.19584 MB per launch of 10000 frame-sets); null for configurations that capture does not cover
+    traffic = 12307234000 + 28195840 if (os.environ.get("MOCAP_PIPELINE") != "split" and BATCH == 10000 and N_CAM == 4) else None
     if rank == 0:
         peak, peak_src = measured_peak()
         # algorithmic bytes: C*W*H bytes per frame-set, read exactly once; a step is split into
@@ -305,7 +309,7 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "matches_resident_path": same},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes) if alg_bytes else None,
                          "avg_launch_ms": kern_ms, "launches_timed": kern_n,
                          "whole_step_frac": (bytes_per_step * args.steps / (ms_total * 1e-3) / 1e9) / peak},

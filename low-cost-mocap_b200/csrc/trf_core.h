@@ -23,7 +23,7 @@
 
 namespace trf {
 
-struct Options { double ftol, xtol, gtol; int max_nfev; };
+struct Options { double ftol, xtol, gtol; int max_nfev; double initial_radius; };   // initial_radius 0: scipy's ||x0||
 struct Report {
     double cost_initial, cost_final, optimality;
     int n_iterations, n_fev, n_jev, status;
@@ -189,7 +189,7 @@ inline int minimize(Problem& prob, double* x, const Options& opt, Report& rep) {
     rep.cost_initial = cost;
     int nfev = 1, njev = 1;
     if (!finite) { rep.status = -1; rep.cost_final = cost; rep.n_fev = nfev; rep.n_jev = njev; rep.n_iterations = 0; rep.optimality = 0; return 0; }
-    double Delta = norm2(x, nf);
+    double Delta = opt.initial_radius > 0.0 ? opt.initial_radius : norm2(x, nf);
     if (Delta == 0.0) Delta = 1.0;
     const int max_nfev = opt.max_nfev > 0 ? opt.max_nfev : nf * 100;
     double alpha = 0.0;

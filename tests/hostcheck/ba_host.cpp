@@ -119,7 +119,7 @@ extern "C" int hc_bundle_adjust(const double* obs, const uint8_t* mask, int m, i
         trf::matrix_to_rotvec(R + 9 * c, q + 1);
         q[4] = t[3 * c]; q[5] = t[3 * c + 1]; q[6] = t[3 * c + 2];
     }
-    trf::Options opt{ftol, 1e-8, 1e-8, max_nfev};
+    trf::Options opt{ftol, 1e-8, 1e-8, max_nfev, 0.0};
     trf::Report rep{};
     int st = trf::minimize(p, x.data(), opt, rep);
     for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
