@@ -138,3 +138,56 @@ extern "C" void hc_rotvec_roundtrip(const double* R, double* rv, double* R2) {
     trf::matrix_to_rotvec(R, rv);
     trf::rotvec_to_matrix(rv, R2);
 }
+
+// ---- generic check of the trust-region control against scipy: an exponential fit with a dead
+//      parameter (rank-deficient Jacobian, like the reference's dead focal entries), Cauchy loss
+namespace {
+struct ExpFit : trf::Problem {
+    std::vector<double> tt, yy;
+    std::vector<int> live_idx;
+    void resid(const double* x, std::vector<double>& f) const {
+        f.resize(tt.size());
+        for (size_t i = 0; i < tt.size(); ++i) f[i] = x[0] * exp(-x[1] * tt[i]) + x[2] - yy[i];     // x[3] is dead
+    }
+    static double cost_of(const std::vector<double>& f) { double c = 0; for (double v : f) c += log1p(v * v); return 0.5 * c; }
+    int trial_cost(const double* x, double* cost, int* finite) override {
+        std::vector<double> f; resid(x, f); *cost = cost_of(f); *finite = 1; return 0;
+    }
+    int linearize(const double* x, double* A, double* g, double* cost, int* finite) override {
+        std::vector<double> f0; resid(x, f0); *cost = cost_of(f0); *finite = 1;
+        const int n = n_live, m = (int)f0.size();
+        std::vector<double> J((size_t)m * n), xp(x, x + n_full), fs(m);
+        for (int j = 0; j < n; ++j) {
+            const int idx = live[j]; const double x0 = x[idx];
+            const double h = 1.4901161193847656e-08 * (x0 >= 0 ? 1.0 : -1.0) * fmax(1.0, fabs(x0));
+            xp[idx] = x0 + h; const double dx = xp[idx] - x0;
+            std::vector<double> f1; resid(xp.data(), f1);
+            for (int i = 0; i < m; ++i) J[(size_t)i * n + j] = (f1[i] - f0[i]) / dx;
+            xp[idx] = x0;
+        }
+        for (int i = 0; i < m; ++i) {
+            const double z = f0[i] * f0[i], t = 1 + z, rho1 = 1 / t, rho2 = -1 / (t * t);
+            double js = rho1 + 2 * rho2 * z; if (js < 2.220446049250313e-16) js = 2.220446049250313e-16; js = sqrt(js);
+            fs[i] = f0[i] * rho1 / js;
+            for (int j = 0; j < n; ++j) J[(size_t)i * n + j] *= js;
+        }
+        for (int a = 0; a < n; ++a) {
+            for (int b = 0; b < n; ++b) { double s = 0; for (int i = 0; i < m; ++i) s += J[(size_t)i * n + a] * J[(size_t)i * n + b]; A[(size_t)a * n + b] = s; }
+            double s = 0; for (int i = 0; i < m; ++i) s += J[(size_t)i * n + a] * fs[i]; g[a] = s;
+        }
+        return 0;
+    }
+};
+}  // namespace
+
+extern "C" int hc_trf_expfit(const double* t, const double* y, int m, double* x /*[4] in/out*/, double ftol, double* report /*[7]*/) {
+    ExpFit p;
+    p.tt.assign(t, t + m); p.yy.assign(y, y + m);
+    p.n_full = 4; p.live_idx = {0, 1, 2}; p.n_live = 3; p.live = p.live_idx.data();
+    trf::Options opt{ftol, 1e-8, 1e-8, 0, 0.0};
+    trf::Report rep{};
+    const int st = trf::minimize(p, x, opt, rep);
+    report[0] = rep.cost_initial; report[1] = rep.cost_final; report[2] = rep.optimality;
+    report[3] = rep.n_iterations; report[4] = rep.n_fev; report[5] = rep.status; report[6] = rep.n_jev;
+    return st;
+}

@@ -2,7 +2,7 @@
 """Secondary (not HBM-bound) figures of SURVEY.md §8(d): per-stage throughput on the shapes of
 BASELINE configs 3 and 5.  Prints one JSON object; run on the GPU box:
 
-    python tools/stage_bench.py > gpurun_out/stage_bench.json
+    python tests/stage_bench.py > gpurun_out/stage_bench.json
 """
 import importlib
 import json
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # tests/ -> repo root
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 

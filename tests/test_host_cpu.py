@@ -146,3 +146,48 @@ def test_header_is_plain_c_and_example_links(built_lib, tmp_path):
     if not torch.cuda.is_available():
         r = subprocess.run([str(exe)], capture_output=True, text=True)
         assert r.returncode == 1 and "no usable CUDA device" in r.stderr      # fails loudly, no CPU fallback
+
+
+@pytest.fixture(scope="module")
+def ba_host():
+    src = os.path.join(ROOT, "tests", "hostcheck", "ba_host.cpp")
+    out = os.path.join(ROOT, "tests", "hostcheck", "libba_host.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-ffp-contract=off", "-o", out, src, "-lm"])
+    return ctypes.CDLL(out)
+
+
+def test_trust_region_control_equals_scipy_on_a_smooth_problem(ba_host):
+    """The optimiser control that drives S4 (csrc/trf_core.h) is a restatement of scipy's trf_no_bounds:
+    on a smooth robust fit with a dead parameter (rank-deficient Jacobian, as in the reference) it must land
+    on scipy's solution with scipy's evaluation count and termination status."""
+    from scipy.optimize import least_squares
+    rng = np.random.default_rng(0)
+    t = np.linspace(0, 4, 40)
+    y = 2.5 * np.exp(-1.3 * t) + 0.5 + rng.normal(0, 0.05, 40)
+    y[::7] += 3.0                                    # outliers for the Cauchy loss
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    ba_host.hc_trf_expfit.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
+    for ftol in (1e-2, 1e-8):
+        x0 = np.array([1.0, 0.5, 0.0, 7.0])
+        ref = least_squares(lambda x: x[0] * np.exp(-x[1] * t) + x[2] - y, x0, loss="cauchy", ftol=ftol)
+        x = x0.copy(); rep = np.zeros(7)
+        assert ba_host.hc_trf_expfit(p(t), p(y), 40, p(x), ftol, p(rep)) == 0
+        assert np.allclose(x, ref.x, rtol=1e-6, atol=1e-8)
+        assert abs(rep[1] - ref.cost) < 1e-9 * max(1.0, ref.cost)
+        assert int(rep[4]) == ref.nfev and int(rep[5]) == ref.status
+
+
+def test_ba_host_model_reaches_reference_quality(ba_host):
+    """Same control on the S4 problem itself (CPU stand-in of the GPU evaluators, float64 differences): from the
+    golden start it reduces the reference's robust cost by orders of magnitude within scipy's evaluation budget."""
+    z = load_golden("ba_c4")
+    C = 4
+    obs = np.ascontiguousarray(z["obs"]); mask = np.ascontiguousarray(z["mask"])
+    K = np.ascontiguousarray(np.tile(z["K"].reshape(1, 9), (C, 1)))
+    R = np.ascontiguousarray(z["R_start"].copy()); t = np.ascontiguousarray(z["t_start"].copy())
+    rep = np.zeros(7)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    ba_host.hc_bundle_adjust.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 3 + [ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    assert ba_host.hc_bundle_adjust(p(obs), p(mask), obs.shape[0], C, p(K), p(R), p(t), 1e-2, 0, p(rep), 1) == 0
+    assert abs(rep[0] - float(z["cost0"])) < 1e-3 * float(z["cost0"])
+    assert rep[1] < 0.5 * rep[0] and int(rep[5]) in (2, 3, 4)
