@@ -18,6 +18,16 @@ __device__ __forceinline__ uint32_t swar_gt(uint32_t w, ThreshConst tc) {
     uint32_t s = (w & 0x7f7f7f7fu) + tc.addc;
     return tc.use_and ? (s & w) : (s | w);
 }
+// "does any of the 16 bytes exceed the threshold?" -- the test every streamed 128-bit word goes through.
+// OR regime (threshold < 128): bit 7 of (s | w) over the four words = bit 7 of (OR of the s) | (OR of the w),
+// so the four ORs are shared: 13 integer ops per 16 pixels.
+template <bool USE_AND>
+__device__ __forceinline__ bool any_above(const uint4& x, ThreshConst tc) {
+    const uint32_t s0 = (x.x & 0x7f7f7f7fu) + tc.addc, s1 = (x.y & 0x7f7f7f7fu) + tc.addc;
+    const uint32_t s2 = (x.z & 0x7f7f7f7fu) + tc.addc, s3 = (x.w & 0x7f7f7f7fu) + tc.addc;
+    if (USE_AND) return (((s0 & x.x) | (s1 & x.y) | (s2 & x.z) | (s3 & x.w)) & 0x80808080u) != 0;
+    return (((s0 | s1 | s2 | s3) | (x.x | x.y | x.z | x.w)) & 0x80808080u) != 0;
+}
 // gathers bit 7 of the four bytes into a nibble (byte 0 -> bit 0)
 __device__ __forceinline__ uint32_t nibble_of(uint32_t hi) {
     return ((((hi >> 7) & 0x01010101u) * 0x00204081u) >> 21) & 0xFu;

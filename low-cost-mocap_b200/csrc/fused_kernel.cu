@@ -18,8 +18,8 @@
 #include "match_device.cuh"
 
 #define FUSED_WARPS 8
-#define FUSED_UNROLL 8
-#define FUSED_SEGS_PER_ITER (32 * FUSED_UNROLL)      // 256 segments = 4 KB per warp iteration
+#define FUSED_UNROLL 6
+#define FUSED_SEGS_PER_ITER (32 * FUSED_UNROLL)      // 192 segments = 3 KB per warp iteration
 
 struct FusedParams {
     const uint4* frames;
@@ -42,7 +42,7 @@ struct FusedParams {
     size_t slab_bytes;
 };
 
-template <bool WIDE>
+template <bool WIDE, bool USE_AND>
 __global__ void __launch_bounds__(FUSED_WARPS * 32, 4)
 k_pipeline_fused(const FusedParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -63,27 +63,39 @@ k_pipeline_fused(const FusedParams P) {
         const uint4* src = P.frames + (size_t)img * P.seg_per_image;
         // rolling window: every lane keeps FUSED_UNROLL 128-bit loads in flight at all times -- an
         // element is consumed and its register immediately re-armed with the load of the next
-        // iteration, so the warp never drains its memory pipeline between iterations
-        uint4 v[FUSED_UNROLL];
+        // iteration, so the warp never drains its memory pipeline between iterations.  Whole
+        // iterations run without bounds checks; a ragged end (seg_per_image % 256 != 0) is handled after.
+        const int n_full = (s_end - s_begin) / FUSED_SEGS_PER_ITER;
+        if (n_full > 0) {
+            const uint4* sp = src + s_begin + lane;
+            uint4 v[FUSED_UNROLL];
 #pragma unroll
-        for (int q = 0; q < FUSED_UNROLL; ++q) {
-            const int si = s_begin + q * 32 + lane;
-            v[q] = (si < s_end) ? ldg_stream(src + si) : make_uint4(0, 0, 0, 0);
-        }
-        for (int s0 = s_begin; s0 < s_end; s0 += FUSED_SEGS_PER_ITER) {
+            for (int q = 0; q < FUSED_UNROLL; ++q) v[q] = ldg_stream(sp + q * 32);
+            for (int it = 0; it < n_full; ++it) {
+                const bool more = it + 1 < n_full;               // warp-uniform
+                const uint4* nx = sp + (it + 1) * FUSED_SEGS_PER_ITER;
 #pragma unroll
-            for (int q = 0; q < FUSED_UNROLL; ++q) {
-                const uint4 x = v[q];
-                const int si = s0 + q * 32 + lane;
-                const int sn = si + FUSED_SEGS_PER_ITER;
-                v[q] = (sn < s_end) ? ldg_stream(src + sn) : make_uint4(0, 0, 0, 0);
-                const uint32_t h0 = swar_gt(x.x, P.tc), h1 = swar_gt(x.y, P.tc);
-                const uint32_t h2 = swar_gt(x.z, P.tc), h3 = swar_gt(x.w, P.tc);
-                if (((h0 | h1 | h2 | h3) & 0x80808080u) == 0) continue;
-                const uint32_t m = nibble_of(h0) | (nibble_of(h1) << 4) | (nibble_of(h2) << 8) | (nibble_of(h3) << 12);
-                const uint32_t slot = atomicAdd(&P.seg_count[img], 1u);
-                if (slot < (uint32_t)P.E) P.seg_list[(size_t)img * P.E + slot] = ((uint32_t)si << 16) | m;
+                for (int q = 0; q < FUSED_UNROLL; ++q) {
+                    if (any_above<USE_AND>(v[q], P.tc)) {         // rare: a marker crosses these 16 pixels
+                        const uint32_t h0 = swar_gt(v[q].x, P.tc), h1 = swar_gt(v[q].y, P.tc);
+                        const uint32_t h2 = swar_gt(v[q].z, P.tc), h3 = swar_gt(v[q].w, P.tc);
+                        const int si = s_begin + it * FUSED_SEGS_PER_ITER + q * 32 + lane;
+                        const uint32_t m = nibble_of(h0) | (nibble_of(h1) << 4) | (nibble_of(h2) << 8) | (nibble_of(h3) << 12);
+                        const uint32_t slot = atomicAdd(&P.seg_count[img], 1u);
+                        if (slot < (uint32_t)P.E) P.seg_list[(size_t)img * P.E + slot] = ((uint32_t)si << 16) | m;
+                    }
+                    if (more) v[q] = ldg_stream(nx + q * 32);     // re-arm this slot at once
+                }
             }
+        }
+        for (int si = s_begin + n_full * FUSED_SEGS_PER_ITER + lane; si < s_end; si += 32) {      // ragged end
+            const uint4 x = ldg_stream(src + si);
+            if (!any_above<USE_AND>(x, P.tc)) continue;
+            const uint32_t h0 = swar_gt(x.x, P.tc), h1 = swar_gt(x.y, P.tc);
+            const uint32_t h2 = swar_gt(x.z, P.tc), h3 = swar_gt(x.w, P.tc);
+            const uint32_t m = nibble_of(h0) | (nibble_of(h1) << 4) | (nibble_of(h2) << 8) | (nibble_of(h3) << 12);
+            const uint32_t slot = atomicAdd(&P.seg_count[img], 1u);
+            if (slot < (uint32_t)P.E) P.seg_list[(size_t)img * P.E + slot] = ((uint32_t)si << 16) | m;
         }
         __threadfence();                                   // release: this warp's list entries
         __syncwarp();
@@ -191,8 +203,13 @@ int launch_pipeline_fused(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int
         CUDA_TRY(ctx, cudaEventRecord(ctx->tim_ev[2 * ctx->tim_used], ctx->stream));
     }
     const int grid = ctx->num_sms * ctx->fused_ctas_per_sm;
-    if (wide) k_pipeline_fused<true><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
-    else k_pipeline_fused<false><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
+    if (wide) {
+        if (P.tc.use_and) k_pipeline_fused<true, true><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
+        else k_pipeline_fused<true, false><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
+    } else {
+        if (P.tc.use_and) k_pipeline_fused<false, true><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
+        else k_pipeline_fused<false, false><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     if (ctx->timing_on) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->tim_ev[2 * ctx->tim_used + 1], ctx->stream));
@@ -212,10 +229,12 @@ int launch_pipeline_fused(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int
 int fused_kernel_init(mocap_ctx* ctx) {
     const size_t smem = fused_slab_bytes(ctx->cfg) * FUSED_WARPS;
     if (smem > 110 * 1024) { ctx->use_fused = 0; return MOCAP_OK; }    // matcher state too large: three-kernel pipeline
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;      // persistent grid = what is actually co-resident
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipeline_fused<false>, FUSED_WARPS * 32, smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipeline_fused<false, false>, FUSED_WARPS * 32, smem));
     if (per_sm < 1) { ctx->use_fused = 0; return MOCAP_OK; }
     ctx->fused_ctas_per_sm = per_sm;
     return MOCAP_OK;
