@@ -148,6 +148,12 @@ MOCAP_API int mocap_set_preprocess(mocap_ctx* ctx, int in_width, int in_height, 
 /* raw uint8 [n_images][in_height][in_width][3] -> out uint8 [n_images][S][S][3].  DEVICE pointers.
  * n_images = n_frame_sets * n_cam (camera index = image index mod n_cam). */
 MOCAP_API int mocap_preprocess_dev(mocap_ctx* ctx, const uint8_t* raw_frames, int n_images, uint8_t* out_frames);
+/* The whole per-frame body of Cameras._camera_read (helpers.py:70-103) for n_frame_sets frame-sets of RAW
+ * camera frames: preprocessing (as mocap_preprocess_dev) -> S1 on the processed 3-channel frames ->
+ * S2+S3.  processed (uint8 [n_images][S][S][3], the frames the reference goes on to JPEG-encode) may be
+ * NULL when the caller does not display them.  DEVICE pointers. */
+MOCAP_API int mocap_pipeline_raw_dev(mocap_ctx* ctx, const uint8_t* raw_frames, int n_frame_sets, int threshold,
+                           uint8_t* processed, double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
 /* The fixed-point undistortion map of one camera as built by mocap_set_preprocess (the tables
  * cv.initUndistortRectifyMap(..., CV_16SC2) returns): m1 int16 [S][S][2], m2 uint16 [S][S].  HOST pointers. */
 MOCAP_API int mocap_get_undistort_map(mocap_ctx* ctx, int cam, int16_t* m1, uint16_t* m2);

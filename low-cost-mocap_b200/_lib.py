@@ -53,6 +53,7 @@ SYMBOLS = {
     "mocap_pipeline_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "mocap_set_preprocess": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "mocap_preprocess_dev": (C.c_int, [_P, _P, C.c_int, _P]),
+    "mocap_pipeline_raw_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "mocap_get_undistort_map": (C.c_int, [_P, C.c_int, _P, _P]),
     "mocap_locate_objects_dev": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "mocap_triangulate_dev": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P]),

@@ -122,6 +122,20 @@ class MocapContext:
         self._check(self.lib.mocap_preprocess_dev(self.h, _ptr(raw.contiguous()), n, _ptr(out)))
         return out
 
+    def pipeline_raw(self, raw, threshold=THRESHOLD, want_frames=False):
+        """Raw camera frames uint8 cuda [B, C, in_h, in_w, 3] -> tracks (and the processed frames)."""
+        torch = _torch()
+        h, w = self._pp_in
+        B = raw.numel() // (self.n_cam * h * w * 3)
+        out = self.alloc_tracks(B, raw.device)
+        frames = torch.empty((B, self.n_cam, self.height, self.width, 3), dtype=torch.uint8, device=raw.device) if want_frames else None
+        self.use_current_stream()
+        self._check(self.lib.mocap_pipeline_raw_dev(self.h, _ptr(raw.contiguous()), B, int(threshold), _ptr(frames),
+                                                    _ptr(out["obj"]), _ptr(out["err"]), _ptr(out["n"]), _ptr(out["flags"])))
+        if want_frames:
+            out["frames"] = frames
+        return out
+
     def undistort_map(self, cam):
         m1 = np.empty((self.height, self.width, 2), dtype=np.int16)
         m2 = np.empty((self.height, self.width), dtype=np.uint16)

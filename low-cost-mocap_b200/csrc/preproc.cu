@@ -224,4 +224,32 @@ int mocap_preprocess_dev(mocap_ctx* ctx, const uint8_t* raw_frames, int n_images
     return MOCAP_OK;
 }
 
+int mocap_pipeline_raw_dev(mocap_ctx* ctx, const uint8_t* raw_frames, int n_frame_sets, int threshold, uint8_t* processed,
+                           double* obj, double* err, int32_t* n_obj, int32_t* set_flags) {
+    if (!ctx) return MOCAP_EINVAL;
+    if (!raw_frames || !obj || !err || !n_obj || n_frame_sets < 0) return mocap_fail(ctx, MOCAP_EINVAL, "mocap_pipeline_raw_dev: bad argument");
+    if (!ctx->d_pp_m1) return mocap_fail(ctx, MOCAP_ESTATE, "mocap_set_preprocess has not been called");
+    if (!ctx->cameras_set) return mocap_fail(ctx, MOCAP_ESTATE, "mocap_set_cameras has not been called");
+    if (n_frame_sets == 0) return MOCAP_OK;
+    const int C = ctx->cfg.n_cam, S = ctx->cfg.width;
+    const size_t img_bytes = (size_t)S * S * 3;
+    const int chunk = 4096 / C > 0 ? 4096 / C : 1;             // frame-sets per launch group (bounded scratch)
+    uint8_t* work = processed;
+    if (!work) {                                               // caller does not want the frames: recycle one chunk of scratch
+        int st = ensure_scratch(ctx, (size_t)chunk * C * img_bytes);
+        if (st) return st;
+        work = static_cast<uint8_t*>(ctx->d_scratch);
+    }
+    for (int s0 = 0; s0 < n_frame_sets; s0 += chunk) {
+        const int ns = n_frame_sets - s0 < chunk ? n_frame_sets - s0 : chunk;
+        uint8_t* dst = processed ? processed + (size_t)s0 * C * img_bytes : work;
+        int st = mocap_preprocess_dev(ctx, raw_frames + (size_t)s0 * C * ctx->pp_in_w * ctx->pp_in_h * 3, ns * C, dst);
+        if (st) return st;
+        st = mocap_pipeline_dev(ctx, dst, ns, 3, threshold, obj + (size_t)s0 * ctx->cfg.max_roots * 3, err + (size_t)s0 * ctx->cfg.max_roots,
+                                n_obj + s0, set_flags ? set_flags + s0 : nullptr);
+        if (st) return st;
+    }
+    return MOCAP_OK;
+}
+
 }  // extern "C"

@@ -668,3 +668,46 @@ def test_plain_c_example_runs(torch, tmp_path):
     for l in lines:
         x, y, z = [float(v) for v in l.split(":")[1].split()[:3]]
         assert abs(x - 0.1) < 0.01 and abs(y - 0.05) < 0.01 and abs(z - 3.0) < 0.05
+
+
+def test_raw_frames_to_tracks_vs_oracle_chain(torch):
+    """helpers.py:70-103 end to end on raw camera frames: preprocess -> _find_dot -> matcher, one C-ABI call,
+    against the same chain of the oracle port."""
+    from oracle.ref_port import RefPort
+    C = 2
+    K = np.array([[320.0, 0, 160], [0, 320, 160], [0, 0, 1]])
+    dist = [-1.26372388e-01, 2.62661497e-01, 1.21306197e-03, 2.24507008e-04, -2.48534118e-01]
+    poses = [{"R": np.eye(3), "t": np.zeros(3)}, {"R": np.eye(3), "t": np.array([-0.4, 0.0, 0.0])}]
+    rng = np.random.default_rng(8)
+    B = 3
+    raw = rng.integers(0, 25, size=(B, C, 240, 320, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[:240, :320]
+    for b in range(B):
+        for m in range(3):
+            X = np.array([rng.uniform(-0.4, 0.4), rng.uniform(-0.25, 0.25), rng.uniform(2.0, 3.0)])
+            for c in range(C):
+                pc = poses[c]["R"] @ X + poses[c]["t"]
+                u, v = 320 * pc[0] / pc[2] + 160, 320 * pc[1] / pc[2] + 160 - 40      # row offset of make_square
+                spot = (255 * np.exp(-((yy - v) ** 2 + (xx - u) ** 2) / (2 * 2.0 ** 2))).astype(np.uint8)
+                raw[b, c] = np.maximum(raw[b, c], spot[:, :, None])
+    ctx = pkg.MocapContext(C, 320, 320, max_blobs=32, max_roots=32)
+    ctx.set_preprocess(320, 240, [0, 0], [K, K], [dist, dist])
+    ctx.set_cameras([K, K], poses)
+    out = ctx.pipeline_raw(torch.from_numpy(raw).cuda(), want_frames=True)
+    port = RefPort([K, K])
+    n = out["n"].cpu().numpy(); obj = out["obj"].cpu().numpy(); frames = out["frames"].cpu().numpy()
+    total = 0
+    for b in range(B):
+        pts = []
+        for c in range(C):
+            f = port.preprocess(raw[b, c], c, dist, 0)
+            assert np.array_equal(frames[b, c], f)
+            pts.append(port.find_dot(f.copy()))
+        e, o, _ = port.match_and_triangulate(pts, poses)
+        assert n[b] == len(e)
+        total += len(e)
+        if len(e):
+            assert np.abs(obj[b, :n[b]] - np.asarray(o, dtype=np.float64)).max() <= X_TOL
+    assert total >= B
+    out2 = ctx.pipeline_raw(torch.from_numpy(raw).cuda())              # without keeping the frames
+    assert np.array_equal(out2["n"].cpu().numpy(), n)
