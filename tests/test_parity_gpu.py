@@ -711,3 +711,44 @@ def test_raw_frames_to_tracks_vs_oracle_chain(torch):
     assert total >= B
     out2 = ctx.pipeline_raw(torch.from_numpy(raw).cuda())              # without keeping the frames
     assert np.array_equal(out2["n"].cpu().numpy(), n)
+
+
+@pytest.mark.parametrize("shape", [(320, 320, 3), (1024, 768, 1), (640, 480, 6), (48, 32, 2)])
+def test_fused_pipeline_other_geometries(torch, monkeypatch, shape):
+    """The fused kernel on image sizes whose segment count is not a multiple of a warp iteration (ragged
+    slices), on the 64-bit-accumulator variant, on tiny frames and on other camera counts: identical to the
+    three-kernel pipeline, and S1 identical to the oracle."""
+    from oracle.ref_port import RefPort
+    W, H, C = shape
+    rng = np.random.default_rng(W + H + C)
+    B = 5
+    frames = rng.integers(0, 40, size=(B, C, H, W), dtype=np.uint8)
+    yy, xx = np.mgrid[:H, :W]
+    for b in range(B):
+        for c in range(C):
+            for _ in range(4):
+                cy, cx, sg = rng.uniform(4, H - 4), rng.uniform(4, W - 4), rng.uniform(1.0, 2.5)
+                spot = (255 * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * sg * sg))).astype(np.uint8)
+                frames[b, c] = np.maximum(frames[b, c], spot)
+    poses = [{"R": np.eye(3), "t": np.array([-0.3 * c, 0.0, 0.0])} for c in range(C)]
+    K = np.array([[W * 0.9, 0, W / 2], [0, W * 0.9, H / 2], [0, 0, 1.0]])
+    res = {}
+    for mode in ("fused", "split"):
+        monkeypatch.setenv("MOCAP_PIPELINE", mode)
+        ctx = pkg.MocapContext(C, W, H, max_blobs=32, max_roots=64)
+        ctx.set_cameras([K] * C, poses)
+        out = ctx.pipeline(torch.from_numpy(frames).cuda())
+        torch.cuda.synchronize()
+        res[mode] = {k: v.cpu().numpy().copy() for k, v in out.items()}
+        if mode == "split":
+            d = ctx.detect(torch.from_numpy(frames).cuda())
+            port = RefPort([K] * C)
+            for i in range(B * C):
+                ref = [p for p in port.find_dot(as3(frames.reshape(-1, H, W)[i])) if p[0] is not None]
+                k = int(d["n"][i])
+                assert d["xy"][i, :k].cpu().numpy().tolist() == ref
+    a, b = res["fused"], res["split"]
+    assert np.array_equal(a["n"], b["n"]) and np.array_equal(a["flags"], b["flags"])
+    for s in range(B):
+        k = a["n"][s]
+        assert np.array_equal(a["obj"][s, :k], b["obj"][s, :k]) and np.array_equal(a["err"][s, :k], b["err"][s, :k])
