@@ -275,9 +275,9 @@ def run_gpu_arm(args):
     kernel_name = ("k_threshold_segments_c1 (three-kernel pipeline)" if os.environ.get("MOCAP_PIPELINE") == "split"
                    else "k_pipeline_fused (threshold + blob reduce + match/DLT in one pass)")
     # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this
-    # workload (profiles/ncu_full_r01_fused.csv: dram__bytes_read.sum 12.307234 GB + dram__bytes_write.sum
-    # 28.19584 MB per launch of 10000 frame-sets); null for configurations that capture does not cover
-    traffic = 12307234000 + 28195840 if (os.environ.get("MOCAP_PIPELINE") != "split" and BATCH == 10000 and N_CAM == 4) else None
+    # workload (profiles/ncu_full_r01_final.csv: dram__bytes_read.sum 12.311724 GB + dram__bytes_write.sum
+    # 30.966272 MB per launch of 10000 frame-sets); null for configurations that capture does not cover
+    traffic = 12311724000 + 30966272 if (os.environ.get("MOCAP_PIPELINE") != "split" and BATCH == 10000 and N_CAM == 4) else None
     if rank == 0:
         peak, peak_src = measured_peak()
         # algorithmic bytes: C*W*H bytes per frame-set, read exactly once; a step is split into
