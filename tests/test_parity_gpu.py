@@ -752,3 +752,99 @@ def test_fused_pipeline_other_geometries(torch, monkeypatch, shape):
     for s in range(B):
         k = a["n"][s]
         assert np.array_equal(a["obj"][s, :k], b["obj"][s, :k]) and np.array_equal(a["err"][s, :k], b["err"][s, :k])
+
+
+def _random_solid_frame(rng, H, W, n_shapes):
+    import cv2
+    img = np.zeros((H, W), np.uint8)
+    for _ in range(n_shapes):
+        cx, cy = int(rng.integers(3, W - 3)), int(rng.integers(3, H - 3))
+        kind = int(rng.integers(0, 4))
+        val = int(rng.integers(52, 256))
+        if kind == 0:
+            cv2.ellipse(img, (cx, cy), (int(rng.integers(1, 9)), int(rng.integers(1, 9))), float(rng.uniform(0, 180)), 0, 360, val, -1)
+        elif kind == 1:
+            x = y = 0
+            for _ in range(int(rng.integers(3, 40))):
+                px, py = np.clip(cx + x, 0, W - 1), np.clip(cy + y, 0, H - 1)
+                img[py, px] = val
+                x += int(rng.integers(-1, 2)); y += int(rng.integers(-1, 2))
+        elif kind == 2:
+            pts = (np.array([[cx, cy]]) + rng.integers(-8, 9, size=(int(rng.integers(3, 7)), 2))).astype(np.int32)
+            cv2.fillPoly(img, [pts], val)
+        else:
+            img[cy:cy + int(rng.integers(1, 6)), cx:cx + int(rng.integers(1, 20))] = val
+    binary = (img > 51).astype(np.uint8)                 # fill holes: the S1 contract is solid blobs
+    ff = binary.copy()
+    cv2.floodFill(ff, np.zeros((H + 2, W + 2), np.uint8), (0, 0), 1)
+    if binary[0, 0]:
+        return None
+    img[ff == 0] = 255
+    return np.maximum(img, rng.integers(0, 52, size=(H, W), dtype=np.uint8))
+
+
+def test_blob_detector_fuzz_vs_cv2(torch):
+    """400 random frames of random solid shapes (ellipses, random walks, polygons, bars; touching, nested in
+    concavities, on the border, 1 px wide): centres, count and order identical to cv2's findContours + moments."""
+    from oracle.ref_port import RefPort
+    rng = np.random.default_rng(2024)
+    H, W = 96, 160
+    frames = []
+    while len(frames) < 400:
+        f = _random_solid_frame(rng, H, W, int(rng.integers(1, 14)))
+        if f is not None:
+            frames.append(f)
+    frames = np.stack(frames)
+    ctx = pkg.MocapContext(1, W, H, max_blobs=64, max_segments=1024)
+    d = ctx.detect(torch.from_numpy(frames).cuda())
+    n = d["n"].cpu().numpy(); xy = d["xy"].cpu().numpy(); fl = d["flags"].cpu().numpy()
+    port = RefPort([np.eye(3)])
+    blobs = 0
+    for i, f in enumerate(frames):
+        ref = [p for p in port.find_dot(as3(f)) if p[0] is not None]
+        assert fl[i] == 0
+        assert xy[i, :n[i]].tolist() == ref, i
+        blobs += len(ref)
+    assert blobs > 1500
+
+
+def test_matcher_fuzz_vs_oracle(torch):
+    """Random blob constellations that do not come from any scene (many wrong correspondences, ragged counts,
+    near-threshold distances to epipolar lines): the kept roots, their order and the chosen points equal the oracle's."""
+    from oracle.ref_port import RefPort
+    rng = np.random.default_rng(77)
+    for C in (3, 5):
+        poses, K = synth.make_rig(C)
+        port = RefPort([K] * C)
+        ctx = _ctx(C, max_blobs=16, max_roots=64, max_cands=16)
+        ctx.set_cameras([K] * C, poses)
+        B, MB = 60, 16
+        xy = np.zeros((B, C, MB, 2), np.int32); n = np.zeros((B, C), np.int32)
+        for b in range(B):
+            # half consistent (a few real 3D points), half clutter
+            pts3 = rng.uniform(-0.5, 0.5, size=(int(rng.integers(0, 5)), 3)) + np.array([0, 0, 3.0])
+            for c in range(C):
+                lst = [list(map(int, synth.project(p[None], poses[c], K)[0])) for p in pts3 if rng.uniform() < 0.85]
+                lst += [[int(rng.integers(100, 540)), int(rng.integers(100, 380))] for _ in range(int(rng.integers(0, 4)))]
+                seen, uniq = set(), []
+                for p in lst:
+                    if tuple(p) not in seen:
+                        seen.add(tuple(p)); uniq.append(p)
+                order = rng.permutation(len(uniq))
+                uniq = [uniq[i] for i in order][:MB]
+                n[b, c] = len(uniq)
+                if uniq:
+                    xy[b, c, :len(uniq)] = uniq
+        d = ctx.match_triangulate(torch.from_numpy(xy.reshape(-1, MB, 2)).cuda(), torch.from_numpy(n.reshape(-1)).cuda())
+        cnt = d["n"].cpu().numpy(); obj = d["obj"].cpu().numpy(); err = d["err"].cpu().numpy()
+        assert (d["flags"].cpu().numpy() == 0).all()
+        for b in range(B):
+            lists = [[list(map(int, xy[b, c, i])) for i in range(n[b, c])] for c in range(C)]
+            e, o, _ = port.match_and_triangulate(lists, poses)
+            assert cnt[b] == len(e), (C, b)
+            if len(e):
+                # wrong correspondences give ill-conditioned triangulations: compare with a relative bar there
+                ref = np.asarray(o, dtype=np.float64)
+                scale = np.maximum(1.0, np.abs(ref).max(axis=1, keepdims=True))
+                assert (np.abs(obj[b, :cnt[b]] - ref) / scale).max() <= 1e-6, (C, b)
+                assert np.allclose(err[b, :cnt[b]], e, rtol=1e-6, atol=1e-9)
