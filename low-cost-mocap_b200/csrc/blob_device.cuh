@@ -86,9 +86,15 @@ __device__ __forceinline__ unsigned block_scan_excl(unsigned v, unsigned& total,
     return base + x - v;
 }
 
+// find with path halving: every visited node is re-pointed at its grandparent.  Concurrent writers only
+// ever replace a parent by one of its own ancestors, so the forest stays valid without locks.
 __device__ __forceinline__ unsigned uf_find(volatile unsigned* parent, unsigned x) {
     unsigned p;
-    while ((p = parent[x]) != x) x = p;
+    while ((p = parent[x]) != x) {
+        const unsigned gp = parent[p];
+        if (gp != p) parent[x] = gp;
+        x = gp;
+    }
     return x;
 }
 // lock-free union keeping the smaller index as representative (root == first run in raster order)
@@ -118,6 +124,9 @@ __device__ __forceinline__ int seg_lower_bound(const uint32_t* seg, int n, uint3
     return lo;
 }
 
+struct BlobSmem;
+__device__ __forceinline__ int row_lower_bound(const BlobSmem& sm, int n, int SPR, bool use_table, int rmin, int rmax, uint32_t pos);
+
 struct BlobSmem {
     uint32_t* seg;        // [E]  sorted (pos<<16)|mask
     unsigned* parent;     // [E]  union-find over runs
@@ -127,7 +136,21 @@ struct BlobSmem {
     uint16_t* rank;       // [E]  blob index of a root run
     unsigned long long* acc;   // [MOCAP_ACC_CAP][4]  A2, SX6, SY6, npix
     unsigned* wsum;       // [32]
+    uint16_t* rowfirst;   // [row_cap] index of the first segment of row (rmin + k), 0xFFFF = empty; nullptr = binary search
+    int row_cap;
 };
+// index of the first segment with position >= pos (pos lies in row pos / SPR): through the per-row index
+// when the image's rows fit it (one load + a scan over that row's few segments), else by binary search
+__device__ __forceinline__ int row_lower_bound(const BlobSmem& sm, int n, int SPR, bool use_table, int rmin, int rmax, uint32_t pos) {
+    if (!use_table) return seg_lower_bound(sm.seg, n, pos);
+    const int r = (int)(pos / (uint32_t)SPR);
+    if (r < rmin || r > rmax) return n;
+    int j = sm.rowfirst[r - rmin];
+    if (j == 0xFFFF) return n;
+    while (j < n && (sm.seg[j] >> 16) < pos) ++j;
+    return j;
+}
+
 inline size_t blob_reduce_smem_bytes(int E) {
     return (size_t)E * (4 + 4 + 2 + 2 + 2 + 2) + (size_t)MOCAP_ACC_CAP * 32 + 32 * 4;
 }
@@ -141,6 +164,7 @@ __device__ __forceinline__ BlobSmem carve_blob_smem(unsigned char* raw, int E) {
     s.node_seg = reinterpret_cast<uint16_t*>(raw);           raw += (size_t)E * 2;
     s.node_bits = reinterpret_cast<uint16_t*>(raw);          raw += (size_t)E * 2;
     s.rank = reinterpret_cast<uint16_t*>(raw);
+    s.rowfirst = nullptr; s.row_cap = 0;
     return s;
 }
 
@@ -162,7 +186,7 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
 
     // ---- 1. raster order of (pos<<16 | mask).  Warp groups (n <= 128): rank sort -- every element
     //         counts the smaller ones (keys are unique), no barriers; CTA groups: bitonic sort.
-    if (NT == 32) {
+    if (NT == 32 && n <= 40) {
         uint32_t* tmp = reinterpret_cast<uint32_t*>(sm.parent);     // free until step 2
         for (int i = tid; i < n; i += NT) {
             const uint32_t e = sm.seg[i];
@@ -172,6 +196,47 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
         }
         gsync<NT>();
         for (int i = tid; i < n; i += NT) sm.seg[i] = tmp[i];
+        gsync<NT>();
+    } else if (NT == 32) {
+        // stable LSD radix sort of the 16-bit positions, 8 bits per pass; histogram in the (not yet used)
+        // accumulator slab, ping-pong between seg[] and the parent[] array
+        uint32_t* hist = reinterpret_cast<uint32_t*>(sm.acc);       // [256]
+        uint32_t* src = sm.seg;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sm.parent);
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            const int shift = 16 + 8 * pass;
+            for (int k = tid; k < 256; k += 32) hist[k] = 0u;
+            gsync<NT>();
+            for (int i = tid; i < n; i += 32) atomicAdd(&hist[(src[i] >> shift) & 0xffu], 1u);
+            gsync<NT>();
+            {   // exclusive scan of the 256 bins: 8 consecutive bins per lane
+                unsigned loc[8], sum = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { loc[k] = hist[tid * 8 + k]; sum += loc[k]; }
+                unsigned tot;
+                unsigned run = block_scan_excl<NT>(sum, tot, sm.wsum);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { hist[tid * 8 + k] = run; run += loc[k]; }
+            }
+            gsync<NT>();
+            for (int i0 = 0; i0 < n; i0 += 32) {                    // stable scatter, 32 elements at a time
+                const int i = i0 + tid;
+                const bool act = i < n;
+                const uint32_t e = act ? src[i] : 0u;
+                const unsigned d = act ? ((e >> shift) & 0xffu) : 0x100u + tid;     // inactive lanes: unique keys
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                const unsigned below = __popc(peers & ((1u << tid) - 1u));
+                unsigned base_pos = 0;
+                if (act) base_pos = hist[d];
+                __syncwarp();
+                if (act && below == 0) hist[d] = base_pos + __popc(peers);
+                if (act) dst[base_pos + below] = e;
+                __syncwarp();
+            }
+            uint32_t* t2 = src; src = dst; dst = t2;
+        }
+        // two passes: the result is back in seg[]
         gsync<NT>();
     } else {
         int n2 = 1;
@@ -191,6 +256,19 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
                 gsync<NT>();
             }
         }
+    }
+
+    // per-row index of the sorted list (neighbour rows are looked up many times per run)
+    const int rmin = (int)((sm.seg[0] >> 16) / (uint32_t)SPR), rmax = (int)((sm.seg[n - 1] >> 16) / (uint32_t)SPR);
+    const bool use_table = sm.rowfirst != nullptr && (rmax - rmin) < sm.row_cap;
+    if (use_table) {
+        for (int k = tid; k <= rmax - rmin; k += NT) sm.rowfirst[k] = 0xFFFFu;
+        gsync<NT>();
+        for (int i = tid; i < n; i += NT) {
+            const int r = (int)((sm.seg[i] >> 16) / (uint32_t)SPR);
+            if (i == 0 || (int)((sm.seg[i - 1] >> 16) / (uint32_t)SPR) != r) sm.rowfirst[r - rmin] = (uint16_t)i;
+        }
+        gsync<NT>();
     }
 
     // ---- 2. runs (maximal horizontal strings of set pixels inside one 16-px segment) become nodes
@@ -240,7 +318,7 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
         if (y > 0) {                                               // the <= 3 segments of row y-1 that touch this run
             const unsigned ext = (rb | (rb << 1) | (rb >> 1)) & 0xffffu;
             const uint32_t q = p - SPR;
-            const int lo = seg_lower_bound(sm.seg, n, sc > 0 ? q - 1 : q);
+            const int lo = row_lower_bound(sm, n, SPR, use_table, rmin, rmax, sc > 0 ? q - 1 : q);
             for (int j = lo; j < n && j < lo + 3; ++j) {
                 const uint32_t ej = sm.seg[j], pj = ej >> 16;
                 if (pj > q + 1) break;
@@ -310,7 +388,7 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
         unsigned Bw = 0;
         if (y + 1 < H) {
             const uint32_t q = p + SPR;
-            const int lo = seg_lower_bound(sm.seg, n, sc > 0 ? q - 1 : q);
+            const int lo = row_lower_bound(sm, n, SPR, use_table, rmin, rmax, sc > 0 ? q - 1 : q);
             for (int j = lo; j < n && j < lo + 3; ++j) {
                 const uint32_t ej = sm.seg[j], pj = ej >> 16;
                 if (pj > q + 1) break;
@@ -401,10 +479,12 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
 
 #define BLOB_WE   256     // segments (and runs) a warp handles
 #define BLOB_WACC 64      // blobs a warp accumulates
+#define BLOB_ROWS 512     // image rows the per-warp row index spans (larger spans fall back to binary search)
 struct WarpSlab {
     unsigned long long acc[BLOB_WACC * 4];
     uint32_t seg[BLOB_WE];
     unsigned parent[BLOB_WE];
     uint16_t base[BLOB_WE], node_seg[BLOB_WE], node_bits[BLOB_WE], rank[BLOB_WE];
+    uint16_t rowfirst[BLOB_ROWS];
 };
 
