@@ -485,6 +485,8 @@ struct WarpSlab {
     uint32_t seg[BLOB_WE];
     unsigned parent[BLOB_WE];
     uint16_t base[BLOB_WE], node_seg[BLOB_WE], node_bits[BLOB_WE], rank[BLOB_WE];
-    uint16_t rowfirst[BLOB_ROWS];
 };
+// The per-row index lives in the upper half of acc[] when the accumulators are 32-bit (they then need
+// only 1 KB of the 2 KB); with 64-bit accumulators the lookup falls back to binary search.
+#define BLOB_ROWFIRST(sl, WIDE) ((WIDE) ? (uint16_t*)nullptr : reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>((sl).acc) + BLOB_WACC * 16))
 

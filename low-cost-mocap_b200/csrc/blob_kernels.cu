@@ -110,7 +110,7 @@ k_blob_reduce_warp(uint32_t* __restrict__ seg_count, const uint32_t* __restrict_
         BlobSmem sm;
         sm.seg = sl.seg; sm.parent = sl.parent; sm.base = sl.base; sm.node_seg = sl.node_seg;
         sm.node_bits = sl.node_bits; sm.rank = sl.rank; sm.acc = sl.acc; sm.wsum = nullptr;
-        sm.rowfirst = sl.rowfirst; sm.row_cap = BLOB_ROWS;
+        sm.rowfirst = BLOB_ROWFIRST(sl, WIDE); sm.row_cap = WIDE ? 0 : BLOB_ROWS;
         const uint32_t* src = seg_list + (size_t)img * E;
         for (int i = lane; i < (int)cnt; i += 32) sm.seg[i] = src[i];
         __syncwarp();
@@ -202,7 +202,7 @@ int launch_detect(mocap_ctx* ctx, const uint8_t* frames, int n_images, int chann
         CUDA_TRY(ctx, cudaEventRecord(ctx->tim_ev[2 * ctx->tim_used + 1], ctx->stream));
         ctx->tim_used += 1;
     }
-    constexpr int WPB = 4;
+    constexpr int WPB = 8;
     const long long mx = c.width > c.height ? c.width : c.height;
     const bool wide = 6ll * mx * c.width * c.height >= (1ll << 32);      // moment sums may exceed 32 bits
     if (wide)
