@@ -9,6 +9,7 @@
 int blob_kernels_init(mocap_ctx* ctx);
 int match_kernels_init(mocap_ctx* ctx);
 int fused_kernel_init(mocap_ctx* ctx);
+int tma_kernel_init(mocap_ctx* ctx);
 
 int mocap_fail(mocap_ctx* ctx, int code, const char* fmt, ...) {
     if (ctx) {
@@ -103,8 +104,11 @@ int mocap_create(mocap_ctx** out, const mocap_config* cfg) {
         {
             const char* mode = getenv("MOCAP_PIPELINE");      // "split": the three-kernel pipeline (for A/B measurements)
             ctx->use_fused = (mode && strcmp(mode, "split") == 0) ? 0 : 1;
+            ctx->use_tma = (mode && strcmp(mode, "tma") == 0) ? 1 : 0;
         }
         if ((st = fused_kernel_init(ctx)) != MOCAP_OK) break;
+        if ((st = tma_kernel_init(ctx)) != MOCAP_OK) break;
+        if (ctx->tma_ctas_per_sm < 1) ctx->use_tma = 0;
     } while (0);
     if (st != MOCAP_OK) { mocap_destroy(ctx); return st; }
     *out = ctx;
@@ -292,7 +296,7 @@ int mocap_pipeline_dev(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets, 
     for (int s0 = 0; s0 < n_frame_sets; s0 += chunk) {
         const int ns = (n_frame_sets - s0 < chunk) ? n_frame_sets - s0 : chunk;
         if (fused) {
-            st = launch_pipeline_fused(ctx, frames + (size_t)s0 * set_bytes, ns, threshold, obj + (size_t)s0 * ctx->cfg.max_roots * 3,
+            st = (ctx->use_tma ? launch_pipeline_tma : launch_pipeline_fused)(ctx, frames + (size_t)s0 * set_bytes, ns, threshold, obj + (size_t)s0 * ctx->cfg.max_roots * 3,
                                        err + (size_t)s0 * ctx->cfg.max_roots, n_obj + s0, set_flags ? set_flags + s0 : nullptr);
             if (st) return st;
             continue;
@@ -348,7 +352,7 @@ int mocap_pipeline_host(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets,
         CUDA_TRY(ctx, cudaEventRecord(copied[k], cs));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, copied[k], 0));
         if (ctx->use_fused && channels == 1) {
-            st = launch_pipeline_fused(ctx, ctx->d_stage[k], ns, threshold, ctx->d_obj + (size_t)s0 * RM * 3, ctx->d_err + (size_t)s0 * RM,
+            st = (ctx->use_tma ? launch_pipeline_tma : launch_pipeline_fused)(ctx, ctx->d_stage[k], ns, threshold, ctx->d_obj + (size_t)s0 * RM * 3, ctx->d_err + (size_t)s0 * RM,
                                        ctx->d_nobj + s0, ctx->d_setflags + s0);
             if (st) break;
             CUDA_TRY(ctx, cudaEventRecord(ctx->stage_free[k], ctx->stream));

@@ -46,6 +46,8 @@ struct mocap_ctx {
     uint32_t* d_set_done;     // fused kernel: [2*cap_images] finished images per set, then deferred marks
     unsigned long long* d_unit_counter;
     int       fused_ctas_per_sm;
+    int       tma_ctas_per_sm;   // 0: bulk-copy kernel unavailable for this configuration
+    int       use_tma;           // MOCAP_PIPELINE=tma: stream through the bulk-copy ring kernel
     int       use_fused;      // 1: single fused pipeline kernel for 1-channel frames (default)
     int32_t*  d_blob_xy;
     int32_t*  d_blob_n;
@@ -92,6 +94,8 @@ int launch_locate(mocap_ctx* ctx, const double* obj, const double* err, const in
 int launch_blob_fallback(mocap_ctx* ctx, int32_t* blob_xy, int32_t* blob_n, int64_t* blob_mom, int32_t* img_flags);
 int launch_match_list(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n, const uint32_t* set_list, uint32_t* set_count,
                       int n_sets_max, double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
+int launch_pipeline_tma(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int threshold,
+                        double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
 int launch_pipeline_fused(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int threshold,
                           double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
 int timing_flush(mocap_ctx* ctx);

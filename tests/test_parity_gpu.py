@@ -848,3 +848,45 @@ def test_matcher_fuzz_vs_oracle(torch):
                 scale = np.maximum(1.0, np.abs(ref).max(axis=1, keepdims=True))
                 assert (np.abs(obj[b, :cnt[b]] - ref) / scale).max() <= 1e-6, (C, b)
                 assert np.allclose(err[b, :cnt[b]], e, rtol=1e-6, atol=1e-9)
+
+
+def test_tma_pipeline_agrees_with_fused(torch, monkeypatch):
+    """MOCAP_PIPELINE=tma (bulk-copy ring kernel) against the default fused kernel: identical bits, including
+    deferred images / frame-sets and a second pass on the same context; also on a ragged image size."""
+    z = load_golden("pipe_c4_m4")
+    C = 4
+    frames = z["frames"][:12].copy()
+    frames[1, 2, 100:160, 40:600] = 255
+    frames[5, 0, 300:304, 100:400] = 255
+    res = {}
+    for mode in ("fused", "tma"):
+        monkeypatch.setenv("MOCAP_PIPELINE", mode)
+        ctx = _ctx(C, max_blobs=64, max_roots=64, max_segments=4096)
+        ctx.set_cameras([z["K"]] * C, poses_from(z))
+        big = torch.from_numpy(np.concatenate([frames] * 40)).cuda()        # 480 frame-sets: every CTA gets work
+        out = ctx.pipeline(big)
+        torch.cuda.synchronize()
+        res[mode] = {k: v.cpu().numpy().copy() for k, v in out.items()}
+        out2 = ctx.pipeline(big)
+        torch.cuda.synchronize()
+        assert np.array_equal(out2["n"].cpu().numpy(), res[mode]["n"])
+    a, b = res["fused"], res["tma"]
+    assert np.array_equal(a["n"], b["n"]) and np.array_equal(a["flags"], b["flags"])
+    mask = np.arange(a["obj"].shape[1])[None, :] < a["n"][:, None]
+    assert np.array_equal(a["obj"][mask], b["obj"][mask]) and np.array_equal(a["err"][mask], b["err"][mask])
+    # ragged chunks: 320x320 -> 6400 segments = 50 chunks of 128
+    rng = np.random.default_rng(5)
+    small = rng.integers(0, 40, size=(30, 2, 320, 320), dtype=np.uint8)
+    small[:, :, 100:104, 50:58] = 255
+    small[:, 1, 200:204, 150:158] = 255
+    K = np.array([[300.0, 0, 160], [0, 300, 160], [0, 0, 1]])
+    poses = [{"R": np.eye(3), "t": np.zeros(3)}, {"R": np.eye(3), "t": np.array([-0.3, 0, 0])}]
+    r2 = {}
+    for mode in ("fused", "tma"):
+        monkeypatch.setenv("MOCAP_PIPELINE", mode)
+        ctx = pkg.MocapContext(2, 320, 320, max_roots=16)
+        ctx.set_cameras([K, K], poses)
+        out = ctx.pipeline(torch.from_numpy(small).cuda())
+        torch.cuda.synchronize()
+        r2[mode] = {k: v.cpu().numpy().copy() for k, v in out.items()}
+    assert np.array_equal(r2["fused"]["n"], r2["tma"]["n"]) and (r2["tma"]["n"] > 0).all()
