@@ -71,7 +71,7 @@ __device__ __forceinline__ bool next_chunk(const FusedParams& P, TmaRing* R, lon
         if (b < total_chunks) { R->cur = b; R->end = min(b + TMA_CHUNKS_PER_UNIT, total_chunks); }
         else R->exhausted = 1;
     }
-    if (R->cur < R->end) { g = R->cur; R->cur = g + 1; R->valid_in_ring += 1; ok = true; }
+    if (R->cur < R->end) { g = R->cur; R->cur = g + 1; atomicAdd(&R->valid_in_ring, 1); ok = true; }   // atomic: consumers decrement outside the lock
     __threadfence_block();
     atomicExch(&R->lock, 0u);
     if (ok) {
