@@ -12,16 +12,21 @@
 //     dedicated producer warp and no empty-barrier;
 //   * a warp that completes an image / a frame-set does the follow-up work (finish_image) while the ring
 //     keeps turning under the other warps.
+// Measured (profiles/README.md): correct (bit-identical to k_pipeline_fused, tests/test_parity_gpu.py) but
+// 2.8x slower on the 4-camera workload (5.4 ms vs 1.94 ms per 10 000 frame-sets): the per-chunk bookkeeping
+// (ticket, hand-out lock, completion atomic with its round trip to L2) costs more than the loads it
+// replaces, and the plain-load kernel already runs at 0.985 of the measured HBM peak.  Kept as the
+// MOCAP_PIPELINE=tma variant, not the default.
 // Hazards: ticket t maps to stage t % NS, generation t / NS.  A consumer first spins on gen[stage] == its
 // generation (published by the refiller after arming the barrier), so it can never look at a barrier more
 // than one phase ahead (the mbarrier parity test only distinguishes adjacent phases).
 #include "fused_common.cuh"
 
 #define TMA_WARPS 8
-#define TMA_NS 8
-#define TMA_CH_SEGS 256                         // 16-pixel segments per chunk
-#define TMA_CH (TMA_CH_SEGS * 16)                // 4 KB
-#define TMA_SLOTS 4                              // units of one CTA that may have chunks in the ring at once
+#define TMA_NS 12
+#define TMA_CH_SEGS 128                         // 16-pixel segments per chunk
+#define TMA_CH (TMA_CH_SEGS * 16)                // 2 KB
+#define TMA_CHUNKS_PER_UNIT 32                   // chunks a CTA claims from the global counter at a time
 
 struct TmaRing {
     unsigned long long full[TMA_NS];             // mbarriers
@@ -29,18 +34,11 @@ struct TmaRing {
     int chunk_img[TMA_NS];                       // image of the chunk in the stage, -1: no more work
     int chunk_off[TMA_NS];                       // first segment of the chunk within its image
     int chunk_len[TMA_NS];                       // segments in the chunk
-    int chunk_slot[TMA_NS];                      // which of the CTA's in-flight units the chunk belongs to
     unsigned ticket;
     unsigned lock;
-    // CTA-local hand-out state (under lock): current unit = chunks [cur, end) of image cur_img; one more unit
-    // is always claimed ahead (nxt_unit) so that the global atomic is never waited for under the lock
-    int cur, end, cur_img, cur_slot;
-    long long nxt_unit;                          // -1: none claimed ahead, -2: the batch is exhausted
+    long long cur, end;                          // CTA-local range of global chunk ids still to hand out
     int exhausted;
     int valid_in_ring;
-    int unit_left[TMA_SLOTS];                    // chunks of the slot's unit not yet consumed
-    int unit_img[TMA_SLOTS];
-    unsigned units_started;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -66,43 +64,24 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 }
 
 // hand out the CTA's next chunk (called by ONE lane).  false: the whole batch has been handed out.
-// A unit is a run of chunks of ONE image (units_per_image units per image), so completion is counted
-// per unit in shared memory and only once per unit in global memory.
-__device__ __forceinline__ bool next_chunk(const FusedParams& P, TmaRing* R, int chunks_per_image,
-                                           int& img, int& off, int& len, int& slot) {
-    bool ok = false, want_claim = false;
-    int idx = 0;
+__device__ __forceinline__ bool next_chunk(const FusedParams& P, TmaRing* R, long long total_chunks, int chunks_per_image,
+                                           int& img, int& off, int& len) {
     while (atomicCAS(&R->lock, 0u, 1u) != 0u) { }
     __threadfence_block();
+    bool ok = false;
+    long long g = 0;
     if (R->cur >= R->end && !R->exhausted) {
-        if (R->nxt_unit >= 0) {                                 // switch to the unit claimed ahead
-            const long long u = R->nxt_unit;
-            const int im = (int)(u / P.units_per_image), k = (int)(u - (long long)im * P.units_per_image);
-            R->cur = k * P.iters_per_unit;
-            R->end = min(R->cur + P.iters_per_unit, chunks_per_image);
-            R->cur_img = im;
-            R->cur_slot = (int)(R->units_started++ % TMA_SLOTS);
-            R->unit_left[R->cur_slot] = R->end - R->cur;
-            R->unit_img[R->cur_slot] = im;
-            R->nxt_unit = -1;
-            want_claim = true;
-        } else if (R->nxt_unit == -2) R->exhausted = 1;
-        // nxt_unit == -1: another lane is fetching it right now -> this call returns "nothing yet" (stage stays empty
-        // for one generation), which costs a trip round the ring but never blocks under the lock
+        const unsigned long long u = atomicAdd(P.unit_counter, 1ull);
+        const long long b = (long long)u * TMA_CHUNKS_PER_UNIT;
+        if (b < total_chunks) { R->cur = b; R->end = min(b + TMA_CHUNKS_PER_UNIT, total_chunks); }
+        else R->exhausted = 1;
     }
-    if (R->cur < R->end) { idx = R->cur; R->cur = idx + 1; img = R->cur_img; slot = R->cur_slot; atomicAdd(&R->valid_in_ring, 1); ok = true; }
+    if (R->cur < R->end) { g = R->cur; R->cur = g + 1; atomicAdd(&R->valid_in_ring, 1); ok = true; }   // atomic: consumers decrement outside the lock
     __threadfence_block();
     atomicExch(&R->lock, 0u);
-    if (want_claim) {                                           // outside the lock: claim the unit after next
-        const unsigned long long u = atomicAdd(P.unit_counter, 1ull);
-        const long long v = (u < (unsigned long long)P.total_units) ? (long long)u : -2;
-        while (atomicCAS(&R->lock, 0u, 1u) != 0u) { }
-        __threadfence_block();
-        R->nxt_unit = v;
-        __threadfence_block();
-        atomicExch(&R->lock, 0u);
-    }
     if (ok) {
+        img = (int)(g / chunks_per_image);
+        const int idx = (int)(g - (long long)img * chunks_per_image);
         off = idx * TMA_CH_SEGS;
         len = min(TMA_CH_SEGS, P.seg_per_image - off);
     }
@@ -111,13 +90,12 @@ __device__ __forceinline__ bool next_chunk(const FusedParams& P, TmaRing* R, int
 
 // (re)fill stage s for generation g: arm its barrier and start the bulk copy, or mark it empty
 __device__ __forceinline__ void fill_stage(const FusedParams& P, TmaRing* R, unsigned char* ring, int s, unsigned g,
-                                           int chunks_per_image) {
-    int img = -1, off = 0, len = 0, slot = 0;
-    const bool ok = next_chunk(P, R, chunks_per_image, img, off, len, slot);
+                                           long long total_chunks, int chunks_per_image) {
+    int img = -1, off = 0, len = 0;
+    const bool ok = next_chunk(P, R, total_chunks, chunks_per_image, img, off, len);
     R->chunk_img[s] = ok ? img : -1;
     R->chunk_off[s] = off;
     R->chunk_len[s] = len;
-    R->chunk_slot[s] = slot;
     if (ok) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // earlier generic reads of the stage vs the async write
         mbar_expect_tx(&R->full[s], (unsigned)len * 16u);
@@ -131,7 +109,7 @@ __device__ __forceinline__ void fill_stage(const FusedParams& P, TmaRing* R, uns
 
 template <bool WIDE, bool USE_AND>
 __global__ void __launch_bounds__(TMA_WARPS * 32, 3)
-k_pipeline_tma(const FusedParams P, int chunks_per_image) {
+k_pipeline_tma(const FusedParams P, long long total_chunks, int chunks_per_image) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* ring = smem_raw;                                         // TMA_NS * TMA_CH, 128-byte aligned
     TmaRing* R = reinterpret_cast<TmaRing*>(smem_raw + (size_t)TMA_NS * TMA_CH);
@@ -141,15 +119,12 @@ k_pipeline_tma(const FusedParams P, int chunks_per_image) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TMA_NS; ++s) { mbar_init(&R->full[s], 1); R->gen[s] = 0xffffffffu; }
-        R->ticket = 0; R->lock = 0; R->cur = 0; R->end = 0; R->cur_img = 0; R->cur_slot = 0; R->exhausted = 0; R->valid_in_ring = 0;
-        R->units_started = 0;
-        const unsigned long long u = atomicAdd(P.unit_counter, 1ull);       // the first unit, claimed ahead like all others
-        R->nxt_unit = (u < (unsigned long long)P.total_units) ? (long long)u : -2;
+        R->ticket = 0; R->lock = 0; R->cur = 0; R->end = 0; R->exhausted = 0; R->valid_in_ring = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (threadIdx.x == 0)
-        for (int s = 0; s < TMA_NS; ++s) fill_stage(P, R, ring, s, 0u, chunks_per_image);
+        for (int s = 0; s < TMA_NS; ++s) fill_stage(P, R, ring, s, 0u, total_chunks, chunks_per_image);
     __syncthreads();
 
     while (true) {
@@ -166,7 +141,7 @@ k_pipeline_tma(const FusedParams P, int chunks_per_image) {
             __syncwarp();
             int leave = 0;
             if (lane == 0) {
-                fill_stage(P, R, ring, s, g + 1u, chunks_per_image);
+                fill_stage(P, R, ring, s, g + 1u, total_chunks, chunks_per_image);
                 leave = (*reinterpret_cast<volatile int*>(&R->exhausted) != 0 &&
                          *reinterpret_cast<volatile int*>(&R->valid_in_ring) == 0) ? 1 : 0;
             }
@@ -193,16 +168,14 @@ k_pipeline_tma(const FusedParams P, int chunks_per_image) {
         }
         __threadfence();                                                    // release: this warp's list entries
         __syncwarp();                                                       // every lane is done reading the stage
-        unsigned done = 0xffffffffu;
+        unsigned done = 0;
         if (lane == 0) {
-            const int slot = *reinterpret_cast<volatile int*>(&R->chunk_slot[s]);
             atomicSub(&R->valid_in_ring, 1);
-            fill_stage(P, R, ring, s, g + 1u, chunks_per_image);                  // the ring keeps turning
-            if (atomicSub(&R->unit_left[slot], 1) == 1)                           // last chunk of its unit in this CTA
-                done = atomicAdd(&P.img_done[img], 1u);
+            fill_stage(P, R, ring, s, g + 1u, total_chunks, chunks_per_image);    // the ring keeps turning
+            done = atomicAdd(&P.img_done[img], 1u);
         }
         done = __shfl_sync(0xffffffffu, done, 0);
-        if (done != (unsigned)P.units_per_image - 1) continue;
+        if (done != (unsigned)chunks_per_image - 1) continue;
         finish_image<WIDE>(P, slab, img, lane);
     }
 }
@@ -223,9 +196,7 @@ int launch_pipeline_tma(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int t
     P.n_sets = n_sets; P.C = c.n_cam; P.W = c.width; P.H = c.height;
     P.seg_per_image = c.width * c.height / MOCAP_SEG_PX;
     const int chunks_per_image = (P.seg_per_image + TMA_CH_SEGS - 1) / TMA_CH_SEGS;
-    P.units_per_image = (chunks_per_image + 15) / 16;            // ~16 chunks (64 KB) per unit, never across images
-    P.iters_per_unit = (chunks_per_image + P.units_per_image - 1) / P.units_per_image;      // chunks per unit
-    P.total_units = (long long)n_sets * c.n_cam * P.units_per_image;
+    const long long total_chunks = (long long)n_sets * c.n_cam * chunks_per_image;
     if (threshold < 0) { P.tc.addc = 0x80808080u; P.tc.use_and = 0; }
     else if (threshold >= 255) { P.tc.addc = 0; P.tc.use_and = 1; }
     else {
@@ -255,11 +226,11 @@ int launch_pipeline_tma(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int t
     }
     const int grid = ctx->num_sms * ctx->tma_ctas_per_sm;
     if (wide) {
-        if (P.tc.use_and) k_pipeline_tma<true, true><<<grid, TMA_WARPS * 32, smem, ctx->stream>>>(P, chunks_per_image);
-        else k_pipeline_tma<true, false><<<grid, TMA_WARPS * 32, smem, ctx->stream>>>(P, chunks_per_image);
+        if (P.tc.use_and) k_pipeline_tma<true, true><<<grid, TMA_WARPS * 32, smem, ctx->stream>>>(P, total_chunks, chunks_per_image);
+        else k_pipeline_tma<true, false><<<grid, TMA_WARPS * 32, smem, ctx->stream>>>(P, total_chunks, chunks_per_image);
     } else {
-        if (P.tc.use_and) k_pipeline_tma<false, true><<<grid, TMA_WARPS * 32, smem, ctx->stream>>>(P, chunks_per_image);
-        else k_pipeline_tma<false, false><<<grid, TMA_WARPS * 32, smem, ctx->stream>>>(P, chunks_per_image);
+        if (P.tc.use_and) k_pipeline_tma<false, true><<<grid, TMA_WARPS * 32, smem, ctx->stream>>>(P, total_chunks, chunks_per_image);
+        else k_pipeline_tma<false, false><<<grid, TMA_WARPS * 32, smem, ctx->stream>>>(P, total_chunks, chunks_per_image);
     }
     CUDA_TRY(ctx, cudaGetLastError());
     if (ctx->timing_on) {
