@@ -181,12 +181,27 @@ def run_gpu_arm(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch N > 1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    frames, truth, poses, K = make_pool()
+    cpu_res = None
+    if rank == 0 and not args.profile:
+        # CPU baseline FIRST, before this process owns a CUDA context and 12 GB of pinned memory (forking
+        # worker processes out of such a process is slow and unsafe): the oracle port on this box's host
+        # cores, bounded sample of the same workload
+        import multiprocessing as mp
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        _W["frames"] = frames
+        mctx = mp.get_context("fork")
+        with mctx.Pool(cores, initializer=_cpu_init, initargs=(K, poses)) as pool_obj:
+            cpu_pass(pool_obj, frames, cores * 2)                  # spin the workers up
+            t_probe, _ = cpu_pass(pool_obj, frames, cores * 2)
+            sample = int(min(BATCH, max(cores * 4, 10.0 / (t_probe / (cores * 2)))))
+            t_cpu, _ = cpu_pass(pool_obj, frames, sample)
+        cpu_res = (cores, sample, t_cpu)
+
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    frames, truth, poses, K = make_pool()
     ctx = pkg.MocapContext(N_CAM, WIDTH, HEIGHT, device=local, max_roots=MAX_ROOTS)
     ctx.set_cameras([K] * N_CAM, poses)
 
@@ -280,20 +295,11 @@ def run_gpu_arm(args):
     traffic = 12311724000 + 30966272 if (os.environ.get("MOCAP_PIPELINE") != "split" and BATCH == 10000 and N_CAM == 4) else None
     if rank == 0:
         peak, peak_src = measured_peak()
-        # algorithmic bytes: C*W*H bytes per frame-set, read exactly once; a step is split into
-        # kern_n / steps launches (4096 frame-sets each), so per launch: step bytes * steps / launches
+        # algorithmic bytes: C*W*H bytes per frame-set, read exactly once; per launch of the timed kernel:
+        # step bytes * steps / launches (one launch per step for the fused kernel, three for the split pipeline)
         alg_bytes = bytes_per_step * args.steps / kern_n if kern_n else None
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
-        # ---- CPU baseline: the oracle port on this box, bounded sample ---------------------
-        import multiprocessing as mp
-        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        _W["frames"] = frames
-        mctx = mp.get_context("fork")
-        with mctx.Pool(cores, initializer=_cpu_init, initargs=(K, poses)) as pool_obj:
-            cpu_pass(pool_obj, frames, cores * 2)                  # spin the workers up
-            t_probe, _ = cpu_pass(pool_obj, frames, cores * 2)
-            sample = int(min(BATCH, max(cores * 4, 10.0 / (t_probe / (cores * 2)))))
-            t_cpu, cpu_points = cpu_pass(pool_obj, frames, sample)
+        cores, sample, t_cpu = cpu_res
         gpu_points = int(out["n"][:1].sum().item())
         line = {
             "metric": "mocap frame-sets/s (4-cam 640x480 synthetic, blob+epipolar+DLT)",
