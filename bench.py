@@ -153,12 +153,12 @@ def run_reference_arm(args):
             t += dt
     value = sample * args.steps / t
     line = {
-        "impl": "reference", "metric": "mocap frame-sets/s (4-cam 640x480 synthetic, blob+epipolar+DLT)",
+        "impl": "reference", "metric": f"mocap frame-sets/s ({N_CAM}-cam 640x480 synthetic, blob+epipolar+DLT)",
         "value": value, "unit": "frame-sets/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 pixels -> int64 moments -> f64 geometry", "data": "synthetic",
-        "config": {"workload": "BASELINE config 2: 4 cameras, 4 markers, 640x480 uint8 frame-sets; "
-                               f"bounded sample of {sample} frame-sets per step of the 10000-frame-set batch",
+        "config": {"workload": f"BASELINE config {'2' if N_CAM == 4 else '3/4 shape'}: {N_CAM} cameras, {N_MARKERS} markers, 640x480 uint8 frame-sets; "
+                               f"bounded sample of {sample} frame-sets per step of the {BATCH}-frame-set batch",
                    "cameras": N_CAM, "markers": N_MARKERS, "frame_sets_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "frame-sets/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} frame-sets per step x {args.steps} steps, one worker process per core"},
@@ -302,14 +302,14 @@ def run_gpu_arm(args):
         cores, sample, t_cpu = cpu_res
         gpu_points = int(out["n"][:1].sum().item())
         line = {
-            "metric": "mocap frame-sets/s (4-cam 640x480 synthetic, blob+epipolar+DLT)",
+            "metric": f"mocap frame-sets/s ({N_CAM}-cam 640x480 synthetic, blob+epipolar+DLT)",
             "value": value, "unit": "frame-sets/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 pixels -> int64 moments -> f64 geometry", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2: 4 cameras, 4 markers, 10000 frame-sets of 640x480 uint8 per GPU per step, "
-                                   "S1 blob + S2 epipolar + S3 DLT",
+            "config": {"workload": (f"BASELINE config {'2' if N_CAM == 4 else '3/4 shape'}: {N_CAM} cameras, {N_MARKERS} markers, {BATCH} frame-sets "
+                                    "of 640x480 uint8 per GPU per step, S1 blob + S2 epipolar + S3 DLT"),
                        "cameras": N_CAM, "markers": N_MARKERS, "frame_sets_per_step_per_gpu": BATCH,
-                       "distinct_frame_sets": POOL, "l2": "inputs (12.3 GB per step) larger than L2, no flush needed",
+                       "distinct_frame_sets": POOL, "l2": f"inputs ({BATCH * N_CAM * 307200 / 1e9:.1f} GB per step) larger than L2, no flush needed",
                        "parallelism": f"frame-set round-robin over {world} GPU(s), one NCCL all-gather of tracks per batch" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "frame-sets/s", "h2d_bytes_per_step": int(bytes_per_step),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "matches_resident_path": same},
@@ -335,9 +335,15 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4m4", choices=["c4m4", "c8m16"],
+                    help="c4m4 (default): BASELINE config 2, the configuration the metric is quoted on; c8m16: the shape of "
+                         "configs 3/4 (8 cameras, 16 markers, 4000 frame-sets per GPU per step) as a secondary figure")
     ap.add_argument("--profile", action="store_true",
                     help="resident steps only (no e2e, no CPU baseline): for runs under ncu; prints no bench line")
     args = ap.parse_args()
+    if args.workload == "c8m16":
+        global N_CAM, N_MARKERS, BATCH, POOL, MAX_ROOTS
+        N_CAM, N_MARKERS, BATCH, POOL, MAX_ROOTS = 8, 16, 4000, 100, 64
     if args.impl == "reference":
         run_reference_arm(args)
     else:
