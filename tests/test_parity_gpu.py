@@ -890,3 +890,46 @@ def test_tma_pipeline_agrees_with_fused(torch, monkeypatch):
         torch.cuda.synchronize()
         r2[mode] = {k: v.cpu().numpy().copy() for k, v in out.items()}
     assert np.array_equal(r2["fused"]["n"], r2["tma"]["n"]) and (r2["tma"]["n"] > 0).all()
+
+
+def test_install_into_patches_a_helpers_like_module(torch):
+    """install_into() on a stand-in for the reference's helpers module (same attribute surface: the Cameras
+    singleton with camera_params, and the module-level hot-path functions): afterwards the module's own names
+    run on the CUDA path with the reference's argument and return conventions."""
+    import types
+    from oracle.ref_port import RefPort
+    C = 4
+    frames, truth, poses, K = synth.make_frame_pool(C, 3, 1, seed=17)
+
+    class _Cams:
+        camera_params = [{"intrinsic_matrix": K.tolist(), "distortion_coef": [0] * 5, "rotation": 0} for _ in range(C)]
+
+    class Cameras:
+        _inst = _Cams()
+
+        @classmethod
+        def instance(cls):
+            return cls._inst
+
+        def _find_dot(self, img):
+            raise AssertionError("not patched")
+    helpers = types.ModuleType("helpers_standin")
+    helpers.Cameras = Cameras
+    for name in ("triangulate_point", "triangulate_points", "calculate_reprojection_error", "calculate_reprojection_errors",
+                 "find_point_correspondance_and_object_points", "bundle_adjustment", "locate_objects"):
+        setattr(helpers, name, None)
+    pkg.install_into(helpers)
+    port = RefPort([K] * C)
+    image_points = []
+    for c in range(C):
+        img, pts = helpers.Cameras._find_dot(Cameras(), as3(frames[0, c]))
+        assert img.shape == (480, 640, 3) and pts == port.find_dot(as3(frames[0, c]))
+        image_points.append(pts)
+    errors, object_points, fr = helpers.find_point_correspondance_and_object_points([list(map(list, p)) for p in image_points], poses, [None] * C)
+    e2, o2, _ = port.match_and_triangulate(image_points, poses)
+    assert isinstance(errors, np.ndarray) and object_points.shape == (len(e2), 3)
+    assert np.abs(object_points - np.asarray(o2, dtype=np.float64)).max() <= X_TOL
+    X = helpers.triangulate_points([[p[0] for p in image_points]], poses)
+    assert X.shape == (1, 3)
+    assert helpers.calculate_reprojection_errors([[p[0] for p in image_points]], X, poses).shape == (1,)
+    assert helpers.locate_objects(object_points, errors) == []
