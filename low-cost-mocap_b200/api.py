@@ -545,7 +545,9 @@ def install_into(helpers_module, session=None):
     """Point a loaded reference ``helpers`` module at the CUDA path."""
     cams = helpers_module.Cameras.instance()
     s = session or MocapSession.install([np.asarray(p["intrinsic_matrix"], dtype=np.float64) for p in cams.camera_params])
-    helpers_module.Cameras._find_dot = lambda self, img: find_dot(img, s)   # Singleton wrapper forwards attribute sets
+    # helpers.Cameras is a Singleton WRAPPER object (Singleton.py:17-37); _camera_read looks _find_dot up on the
+    # decorated class of the instance, so that is where the replacement goes
+    type(cams)._find_dot = lambda self, img: find_dot(img, s)
     helpers_module.triangulate_point = lambda ip, cp: triangulate_point(ip, cp, s)
     helpers_module.triangulate_points = lambda ip, cp: triangulate_points(ip, cp, s)
     helpers_module.calculate_reprojection_error = lambda ip, op, cp: calculate_reprojection_error(ip, op, cp, s)

@@ -154,3 +154,32 @@ def test_calibrate_init_equals_live_reference(synth):
     for a, b in zip(mine, captured["poses"]):
         assert np.array_equal(np.asarray(a["R"], dtype=np.float64), b["R"])
         assert np.array_equal(np.asarray(a["t"], dtype=np.float64).ravel(), b["t"].ravel())
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree only exists in the build container")
+def test_install_into_rebinds_the_live_reference_module():
+    """install_into() must replace exactly the names the reference's callers resolve at call
+    time -- the method on the class behind the Singleton wrapper and the module-level functions."""
+    import importlib
+    pkg = importlib.import_module("low-cost-mocap_b200")
+    helpers, cams = ref_harness.load_reference(4)
+    names = ["triangulate_point", "triangulate_points", "calculate_reprojection_error", "calculate_reprojection_errors",
+             "find_point_correspondance_and_object_points", "bundle_adjustment", "locate_objects"]
+    saved = {n: getattr(helpers, n) for n in names}
+    saved_fd = type(cams)._find_dot
+    try:
+        s = pkg.install_into(helpers)
+        assert len(s.intrinsics) == 4 and np.array_equal(s.intrinsics[0], np.asarray(cams.camera_params[0]["intrinsic_matrix"]))
+        assert type(cams)._find_dot is not saved_fd
+        assert cams._find_dot.__func__ is type(cams)._find_dot          # what _camera_read will call (helpers.py:87)
+        for n in names:
+            assert getattr(helpers, n) is not saved[n]
+        # without a GPU the replacements fail loudly instead of falling back
+        import torch
+        if not torch.cuda.is_available():
+            with pytest.raises(Exception):
+                helpers.triangulate_points([[[1, 2], [3, 4], [None, None], [None, None]]], [{"R": np.eye(3), "t": np.zeros(3)}] * 4)
+    finally:
+        for n in names:
+            setattr(helpers, n, saved[n])
+        type(cams)._find_dot = saved_fd

@@ -922,7 +922,7 @@ def test_install_into_patches_a_helpers_like_module(torch):
     port = RefPort([K] * C)
     image_points = []
     for c in range(C):
-        img, pts = helpers.Cameras._find_dot(Cameras(), as3(frames[0, c]))
+        img, pts = helpers.Cameras.instance()._find_dot(as3(frames[0, c]))
         assert img.shape == (480, 640, 3) and pts == port.find_dot(as3(frames[0, c]))
         image_points.append(pts)
     errors, object_points, fr = helpers.find_point_correspondance_and_object_points([list(map(list, p)) for p in image_points], poses, [None] * C)
