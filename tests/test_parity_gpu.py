@@ -850,6 +850,8 @@ def test_matcher_fuzz_vs_oracle(torch):
                 assert np.allclose(err[b, :cnt[b]], e, rtol=1e-6, atol=1e-9)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("MOCAP_TEST_TMA") != "1",
+                    reason="experimental bulk-copy variant (not the default pipeline): run with MOCAP_TEST_TMA=1")
 def test_tma_pipeline_agrees_with_fused(torch, monkeypatch):
     """MOCAP_PIPELINE=tma (bulk-copy ring kernel) against the default fused kernel: identical bits, including
     deferred images / frame-sets and a second pass on the same context; also on a ragged image size."""
