@@ -935,3 +935,23 @@ def test_install_into_patches_a_helpers_like_module(torch):
     assert X.shape == (1, 3)
     assert helpers.calculate_reprojection_errors([[p[0] for p in image_points]], X, poses).shape == (1,)
     assert helpers.locate_objects(object_points, errors) == []
+
+
+def test_error_behaviour(torch):
+    """C-ABI status codes surface as MocapError with the library's message; nothing falls back silently."""
+    with pytest.raises(pkg.MocapError):
+        pkg.MocapContext(0)                                    # invalid configuration
+    with pytest.raises(pkg.MocapError):
+        pkg.MocapContext(4, 641, 480)                          # width must be a multiple of 16
+    ctx = _ctx(2)
+    frames = torch.zeros((1, 2, 480, 640), dtype=torch.uint8, device="cuda")
+    with pytest.raises(pkg.MocapError) as ei:
+        ctx.pipeline(frames)                                   # cameras not set
+    assert "mocap_set_cameras" in str(ei.value)
+    with pytest.raises(pkg.MocapError):
+        ctx.preprocess(torch.zeros((2, 240, 320, 3), dtype=torch.uint8, device="cuda"))   # preprocessing not set
+    with pytest.raises(pkg.MocapError):
+        ctx.set_preprocess(320, 240, [0, 0], [np.eye(3)] * 2, [[0] * 5] * 2)              # context is not square
+    ctx.set_cameras([np.eye(3)] * 2, [{"R": np.eye(3), "t": np.zeros(3)}] * 2)
+    out = ctx.pipeline(frames)                                 # empty frames: zero points, no error
+    assert int(out["n"][0]) == 0 and int(out["flags"][0]) == 0
