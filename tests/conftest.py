@@ -21,3 +21,13 @@ def synth():
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_collection_modifyitems(config, items):
+    """A GPU test that wedges (a hung kernel, a dead box) must fail, not stall the whole run: 10-minute cap per
+    GPU test when pytest-timeout is available."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(600))
