@@ -59,6 +59,7 @@ class MocapContext:
         self.n_cam, self.width, self.height = n_cam, width, height
         self.device = device
         self._tdev = None
+        self._pp_in = None
 
     # -- lifetime -------------------------------------------------------------------------
     def close(self):
@@ -115,6 +116,8 @@ class MocapContext:
     def preprocess(self, raw):
         """raw uint8 cuda tensor [..., in_h, in_w, 3] (whole frame-sets) -> uint8 [N, S, S, 3]."""
         torch = _torch()
+        if self._pp_in is None:
+            raise MocapError(-5, "mocap_set_preprocess has not been called (MocapContext.set_preprocess)")
         h, w = self._pp_in
         n = raw.numel() // (h * w * 3)
         out = torch.empty((n, self.height, self.width, 3), dtype=torch.uint8, device=raw.device)
@@ -125,6 +128,8 @@ class MocapContext:
     def pipeline_raw(self, raw, threshold=THRESHOLD, want_frames=False):
         """Raw camera frames uint8 cuda [B, C, in_h, in_w, 3] -> tracks (and the processed frames)."""
         torch = _torch()
+        if self._pp_in is None:
+            raise MocapError(-5, "mocap_set_preprocess has not been called (MocapContext.set_preprocess)")
         h, w = self._pp_in
         B = raw.numel() // (self.n_cam * h * w * 3)
         out = self.alloc_tracks(B, raw.device)
