@@ -21,10 +21,8 @@
 #define PP_G (PP_T + 4)             // blurred region needed by the 5x5 filter
 #define PP_U (PP_T + 12)            // undistorted region needed by the 9x9 blur of that
 
-struct PreprocTables {
-    int16_t* m1;      // [C][S][S][2]  integer source coordinates (x, y)
-    uint16_t* m2;     // [C][S][S]     (fy << 5) | fx, 1/32 px fractions
-};
+// undistortion map per camera: m1 int16 [S][S][2] integer source coordinates (x, y);
+//                            m2 uint16 [S][S]   (fy << 5) | fx, the 1/32 px fractions
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
