@@ -130,6 +130,27 @@ def cpu_pass(pool_obj, frames, n_sets):
     return time.perf_counter() - t0, sum(got)
 
 
+def check_against_oracle(frames, poses, K, out, n_check=8):
+    """3D-point distance to the reference (oracle port) on the first frame-sets of the batch the timed steps
+    processed (rank 0's shard starts with pool frame-sets 0, world, 2*world, ...; at N = 1 these are 0..n-1)."""
+    from oracle.ref_port import RefPort
+    port = RefPort([K] * len(poses))
+    n = out["n"][:n_check].cpu().numpy()
+    obj = out["obj"][:n_check].cpu().numpy()
+    worst, same_count, points = 0.0, True, 0
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    for b in range(n_check):
+        fs = frames[(b * world) % len(frames)]
+        pts = [port.find_dot(np.repeat(img[:, :, None], 3, axis=2)) for img in fs]
+        e, o, _ = port.match_and_triangulate(pts, poses)
+        same_count = same_count and (len(e) == int(n[b]))
+        if len(e) and len(e) == int(n[b]):
+            worst = max(worst, float(np.abs(obj[b, :len(e)] - np.asarray(o, dtype=np.float64)).max()))
+            points += len(e)
+    return {"frame_sets": n_check, "points": points, "point_counts_equal": bool(same_count),
+            "max_abs_3d_difference": worst, "tolerance": 1e-7}
+
+
 def run_reference_arm(args):
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
@@ -196,7 +217,14 @@ def run_gpu_arm(args):
             t_probe, _ = cpu_pass(pool_obj, frames, cores * 2)
             sample = int(min(BATCH, max(cores * 4, 10.0 / (t_probe / (cores * 2)))))
             t_cpu, _ = cpu_pass(pool_obj, frames, sample)
-        cpu_res = (cores, sample, t_cpu)
+        # the reference itself is single-threaded Python: one core, a few seconds, in this process
+        _cpu_init(K, poses)
+        t0 = time.perf_counter()
+        n_single = 0
+        while time.perf_counter() - t0 < 3.0:
+            _cpu_one(n_single)
+            n_single += 1
+        cpu_res = (cores, sample, t_cpu, n_single / (time.perf_counter() - t0))
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -299,7 +327,8 @@ def run_gpu_arm(args):
         # step bytes * steps / launches (one launch per step for the fused kernel, three for the split pipeline)
         alg_bytes = bytes_per_step * args.steps / kern_n if kern_n else None
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
-        cores, sample, t_cpu = cpu_res
+        cores, sample, t_cpu, single_core = cpu_res
+        parity = check_against_oracle(frames, poses, K, out)
         gpu_points = int(out["n"][:1].sum().item())
         line = {
             "metric": f"mocap frame-sets/s ({N_CAM}-cam 640x480 synthetic, blob+epipolar+DLT)",
@@ -320,7 +349,9 @@ def run_gpu_arm(args):
                          "avg_launch_ms": kern_ms, "launches_timed": kern_n,
                          "whole_step_frac": (bytes_per_step * args.steps / (ms_total * 1e-3) / 1e9) / peak},
             "cpu_baseline": {"value": sample / t_cpu, "unit": "frame-sets/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} frame-sets of the same workload, one worker process per core"},
+                             "sample": f"{sample} frame-sets of the same workload, one worker process per core",
+                             "single_core_value": single_core},
+            "parity_vs_oracle": parity,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
