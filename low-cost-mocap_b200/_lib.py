@@ -77,9 +77,10 @@ def load():
     """dlopen the in-tree library and type every symbol.  Raises if it is not built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise MocapError(-2, f"{LIB_PATH} is not built (run python __graft_entry__.py build); there is no CPU fallback")
-        lib = C.CDLL(LIB_PATH)
+        path = os.environ.get("MOCAP_B200_LIB", LIB_PATH)        # a differently-built libmocap_b200.so (tuning runs)
+        if not os.path.exists(path):
+            raise MocapError(-2, f"{path} is not built (run python __graft_entry__.py build); there is no CPU fallback")
+        lib = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype = res

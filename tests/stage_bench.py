@@ -132,6 +132,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "config3":      # for ncu: just the 8-camera pipeline
         print(json.dumps(config3_pipeline()))
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
+        print(json.dumps(preprocess_rate()))
+        sys.exit(0)
     out = {"preprocess": preprocess_rate(),"config3_pipeline": config3_pipeline(), "dlt": dlt_rate(),
            "ba_config3_batch": ba_case(8, 16000, "config 3 per-batch BA: 8 cameras, 1000 frames x 16 markers = 16000 tracked points"),
            "ba_config5": ba_case(16, 6400, "config 5 cold start: 16 cameras, 64 markers x 100 frames = 6400 tracked points")}

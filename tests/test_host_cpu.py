@@ -191,3 +191,37 @@ def test_ba_host_model_reaches_reference_quality(ba_host):
     assert ba_host.hc_bundle_adjust(p(obs), p(mask), obs.shape[0], C, p(K), p(R), p(t), 1e-2, 0, p(rep), 1) == 0
     assert abs(rep[0] - float(z["cost0"])) < 1e-3 * float(z["cost0"])
     assert rep[1] < 0.5 * rep[0] and int(rep[5]) in (2, 3, 4)
+
+
+@pytest.fixture(scope="module")
+def preproc_host():
+    src = os.path.join(ROOT, "tests", "hostcheck", "preproc_host.cpp")
+    out = os.path.join(ROOT, "tests", "hostcheck", "libpreproc_host.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-fno-strict-aliasing", "-o", out, src])
+    return ctypes.CDLL(out)
+
+
+@pytest.mark.parametrize("S,in_h,rot,word_stores,n_threads", [(320, 240, 0, 1, 256), (320, 240, 2, 0, 256), (200, 150, 2, 1, 96),
+                                                               (90, 70, 0, 0, 256), (70, 40, 0, 0, 64)])
+def test_preprocess_tile_stages_equal_cv2_chain_on_host(preproc_host, S, in_h, rot, word_stores, n_threads):
+    """The tile stages the preprocessing kernel is made of (csrc/preproc_tile.cuh: packed 4-way / 2-way dot
+    products, mirrored apron, transposed Q8.8 plane) stepped through on the host equal helpers.py:70-82 as
+    restated by the oracle port, bit for bit: noise frames (worst case for every rounding), a saturated
+    frame, sizes that are not a multiple of the tile, both rotations, both store paths."""
+    import cv2
+    from oracle.ref_port import RefPort
+    f0 = float(S)
+    K = np.array([[f0, 0, S / 2.0], [0, f0, S / 2.0], [0, 0, 1]])
+    dist = np.array([-1.26372388e-01, 2.62661497e-01, 1.21306197e-03, 2.24507008e-04, -2.48534118e-01]) * (1.0 if rot == 0 else 2.5)
+    m1, m2 = cv2.initUndistortRectifyMap(K, dist, np.eye(3), K, (S, S), cv2.CV_16SC2)
+    m1 = np.ascontiguousarray(m1); m2 = np.ascontiguousarray(m2)
+    port = RefPort([K])
+    rng = np.random.default_rng(S + rot)
+    frames = [rng.integers(0, 256, size=(in_h, S, 3), dtype=np.uint8), np.full((in_h, S, 3), 255, dtype=np.uint8),
+              (rng.integers(0, 2, size=(in_h, S, 3)) * 255).astype(np.uint8)]
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for raw in frames:
+        want = port.preprocess(raw, 0, dist, rot)
+        got = np.full((S, S, 3), 7, dtype=np.uint8)
+        preproc_host.hc_preprocess(p(raw), S, in_h, S, rot, p(m1), p(m2), p(got), word_stores if S % 4 == 0 else 0, n_threads)
+        assert np.array_equal(got, want), (np.argwhere(got != want)[:5], int((got != want).sum()))
