@@ -25,7 +25,6 @@ int ensure_scratch(mocap_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->scratch_bytes) return MOCAP_OK;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->d_scratch);
-    cudaFree(ctx->d_pp_m1); cudaFree(ctx->d_pp_m2); cudaFree(ctx->d_pp_rot);
     ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_scratch, bytes));
     ctx->scratch_bytes = bytes;

@@ -3,7 +3,7 @@
 // Replaces the per-camera body of Cameras._camera_read (reference computer_code/api/helpers.py:70-82):
 //   rot90 -> make_square (zero pad to a square + 8-row feather, helpers.py:507-523) -> cv.undistort ->
 //   cv.GaussianBlur 9x9 (sigma 0) -> cv.filter2D with the 5x5 sharpening kernel -> cvtColor RGB2BGR
-// as ONE kernel per batch of frames: every CTA produces a 64x32 output tile and keeps all
+// as ONE kernel per batch of frames: every CTA produces a 64x64 output tile and keeps all
 // intermediates in shared memory, so a raw frame is read once and the processed frame written once
 // (the reference makes five full passes over every frame on the CPU).
 //
@@ -21,12 +21,13 @@
 // undistortion map per camera: m1 int16 [S][S][2] integer source coordinates (x, y), read by the kernel as
 //                            one 32-bit word per pixel;  m2 uint16 [S][S]   (fy << 5) | fx, the 1/32 px fractions
 //
-// One CTA = one 64x32 output tile (preproc_tile.cuh): four stages separated by barriers, 28 KB of shared
-// memory and 40 registers, so 6 CTAs are resident per SM and one CTA's gather overlaps its neighbours'
-// filter stages.
+// One CTA = one 64x64 output tile (preproc_tile.cuh): four stages separated by barriers, 48 KB of shared
+// memory and 46 registers, so 4 CTAs are resident per SM and one CTA's gather overlaps its neighbours'
+// filter stages.  (A 64x32 tile keeps 7 CTAs resident but undistorts 16 % more apron pixels: 8 % slower.)
 __global__ void __launch_bounds__(256)
 k_preprocess(const uint8_t* __restrict__ raw_frames, int C, int in_w, int in_h, int S, const int* __restrict__ rotation,
-             const int32_t* __restrict__ m1, const uint16_t* __restrict__ m2, uint8_t* __restrict__ out, int word_stores) {
+             const int32_t* __restrict__ m1, const uint16_t* __restrict__ m2, uint8_t* __restrict__ out, uint8_t* __restrict__ gray,
+             int word_stores) {
     __shared__ __align__(16) uint8_t smem[PP_SMEM_BYTES];
     uint8_t* U = smem;
     uint32_t* GhT = reinterpret_cast<uint32_t*>(smem + PP_U_BYTES);
@@ -36,16 +37,22 @@ k_preprocess(const uint8_t* __restrict__ raw_frames, int C, int in_w, int in_h, 
     PPFrame f;
     f.raw = raw_frames + (size_t)img * in_w * in_h * 3;
     f.m1 = m1; f.m2 = m2; f.map_offset = cam * S * S;
-    f.out = out + (size_t)img * S * S * 3;
+    f.out = out ? out + (size_t)img * S * S * 3 : nullptr;
+    f.gray = gray ? gray + (size_t)img * S * S : nullptr;
     f.in_w = in_w; f.in_h = in_h; f.S = S; f.rot = rotation[cam]; f.ay = (S - in_h) / 2;
     f.word_stores = word_stores;
-    pp_stage_undistort(f, U, x0, y0, threadIdx.x, blockDim.x);
+    // the thread index is made opaque: knowing it is below 1024 the compiler narrows the item arithmetic of
+    // the stages to 16 bits, which costs more mask/extend instructions than it saves
+    int tid = threadIdx.x;
+    asm volatile("" : "+r"(tid));
+    const int nt = 256;
+    pp_stage_undistort(f, U, x0, y0, tid, nt);
     __syncthreads();
-    pp_stage_blur_h(U, GhT, threadIdx.x, blockDim.x);
+    pp_stage_blur_h(U, GhT, tid, nt);
     __syncthreads();
-    pp_stage_blur_v(GhT, G, threadIdx.x, blockDim.x);
+    pp_stage_blur_v(GhT, G, tid, nt);
     __syncthreads();
-    pp_stage_sharpen_store(f, G, x0, y0, threadIdx.x, blockDim.x);
+    pp_stage_sharpen_store(f, G, x0, y0, tid, nt);
 }
 
 // cv.initUndistortRectifyMap(K, dist, I, K, (S, S), CV_16SC2): per output pixel the source position
@@ -115,21 +122,30 @@ int mocap_get_undistort_map(mocap_ctx* ctx, int cam, int16_t* m1, uint16_t* m2) 
     return MOCAP_OK;
 }
 
+// processed frames and/or the grayscale plane S1 derives from them
+static int launch_preprocess(mocap_ctx* ctx, const uint8_t* raw_frames, int n_images, uint8_t* out_frames, uint8_t* gray) {
+    const int S = ctx->cfg.width;
+    for (int i0 = 0; i0 < n_images; i0 += 65535) {            // gridDim.z
+        const int n = n_images - i0 < 65535 ? n_images - i0 : 65535;
+        uint8_t* o = out_frames ? out_frames + (size_t)i0 * S * S * 3 : nullptr;
+        uint8_t* g = gray ? gray + (size_t)i0 * S * S : nullptr;
+        const int word_stores = (S % 4 == 0) && (reinterpret_cast<uintptr_t>(o) % 4 == 0) && (reinterpret_cast<uintptr_t>(g) % 4 == 0);
+        k_preprocess<<<dim3((S + PP_TX - 1) / PP_TX, (S + PP_TY - 1) / PP_TY, n), 256, 0, ctx->stream>>>(
+            raw_frames + (size_t)i0 * ctx->pp_in_w * ctx->pp_in_h * 3, ctx->cfg.n_cam, ctx->pp_in_w, ctx->pp_in_h, S, ctx->d_pp_rot,
+            reinterpret_cast<const int32_t*>(ctx->d_pp_m1), ctx->d_pp_m2, o, g, word_stores);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
+    return MOCAP_OK;
+}
+
 int mocap_preprocess_dev(mocap_ctx* ctx, const uint8_t* raw_frames, int n_images, uint8_t* out_frames) {
     if (!ctx) return MOCAP_EINVAL;
     if (!raw_frames || !out_frames || n_images < 0) return mocap_fail(ctx, MOCAP_EINVAL, "mocap_preprocess_dev: bad argument");
     if (!ctx->d_pp_m1) return mocap_fail(ctx, MOCAP_ESTATE, "mocap_set_preprocess has not been called");
     if (n_images == 0) return MOCAP_OK;
-    if (n_images > 65535) return mocap_fail(ctx, MOCAP_EINVAL, "mocap_preprocess_dev: at most 65535 images per call");
     CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
-    const int S = ctx->cfg.width;
-    const int word_stores = (S % 4 == 0) && (reinterpret_cast<uintptr_t>(out_frames) % 4 == 0);
-    k_preprocess<<<dim3((S + PP_TX - 1) / PP_TX, (S + PP_TY - 1) / PP_TY, n_images), 256, 0, ctx->stream>>>(
-        raw_frames, ctx->cfg.n_cam, ctx->pp_in_w, ctx->pp_in_h, S, ctx->d_pp_rot, reinterpret_cast<const int32_t*>(ctx->d_pp_m1),
-        ctx->d_pp_m2, out_frames, word_stores);
-    CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches += 1;
-    return MOCAP_OK;
+    return launch_preprocess(ctx, raw_frames, n_images, out_frames, nullptr);
 }
 
 int mocap_pipeline_raw_dev(mocap_ctx* ctx, const uint8_t* raw_frames, int n_frame_sets, int threshold, uint8_t* processed,
@@ -140,20 +156,21 @@ int mocap_pipeline_raw_dev(mocap_ctx* ctx, const uint8_t* raw_frames, int n_fram
     if (!ctx->cameras_set) return mocap_fail(ctx, MOCAP_ESTATE, "mocap_set_cameras has not been called");
     if (n_frame_sets == 0) return MOCAP_OK;
     const int C = ctx->cfg.n_cam, S = ctx->cfg.width;
-    const size_t img_bytes = (size_t)S * S * 3;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+    // The preprocessing kernel also emits the grayscale plane _find_dot would derive from the processed frame
+    // (helpers.py:144), so S1-S3 run on 1 byte per pixel through the single-pass pipeline kernel; the
+    // processed BGR frames are only written when the caller asks for them.
+    const size_t gray_bytes = (size_t)S * S;
     const int chunk = 4096 / C > 0 ? 4096 / C : 1;             // frame-sets per launch group (bounded scratch)
-    uint8_t* work = processed;
-    if (!work) {                                               // caller does not want the frames: recycle one chunk of scratch
-        int st = ensure_scratch(ctx, (size_t)chunk * C * img_bytes);
-        if (st) return st;
-        work = static_cast<uint8_t*>(ctx->d_scratch);
-    }
+    int st = ensure_scratch(ctx, (size_t)chunk * C * gray_bytes);
+    if (st) return st;
+    uint8_t* gray = static_cast<uint8_t*>(ctx->d_scratch);
     for (int s0 = 0; s0 < n_frame_sets; s0 += chunk) {
         const int ns = n_frame_sets - s0 < chunk ? n_frame_sets - s0 : chunk;
-        uint8_t* dst = processed ? processed + (size_t)s0 * C * img_bytes : work;
-        int st = mocap_preprocess_dev(ctx, raw_frames + (size_t)s0 * C * ctx->pp_in_w * ctx->pp_in_h * 3, ns * C, dst);
+        st = launch_preprocess(ctx, raw_frames + (size_t)s0 * C * ctx->pp_in_w * ctx->pp_in_h * 3, ns * C,
+                               processed ? processed + (size_t)s0 * C * gray_bytes * 3 : nullptr, gray);
         if (st) return st;
-        st = mocap_pipeline_dev(ctx, dst, ns, 3, threshold, obj + (size_t)s0 * ctx->cfg.max_roots * 3, err + (size_t)s0 * ctx->cfg.max_roots,
+        st = mocap_pipeline_dev(ctx, gray, ns, 1, threshold, obj + (size_t)s0 * ctx->cfg.max_roots * 3, err + (size_t)s0 * ctx->cfg.max_roots,
                                 n_obj + s0, set_flags ? set_flags + s0 : nullptr);
         if (st) return st;
     }

@@ -30,13 +30,13 @@
 
 #define PP_TX 64
 #ifndef PP_TY
-#define PP_TY 32                           // multiple of 4
+#define PP_TY 64                           // multiple of 4 (64x64: 48 KB of shared memory, 1.41x apron overhead; 64x32: 28 KB, 1.63x)
 #endif
 #define PP_UW (PP_TX + 12)                 // 76 bytes = 19 words per row
-#define PP_UH (PP_TY + 12)                 // 44 rows = 22 row pairs
+#define PP_UH (PP_TY + 12)                 // 76 rows = 38 row pairs
 #define PP_GW (PP_TX + 4)                  // 68 = 17 groups of 4
-#define PP_GH (PP_TY + 4)                  // 36 = 9 groups of 4
-#define PP_GHT_STRIDE (PP_UH / 2 + 1)      // 23 words per column: odd, so column-parallel access is conflict free
+#define PP_GH (PP_TY + 4)                  // 68 = 17 groups of 4
+#define PP_GHT_STRIDE (PP_UH / 2 + 1)      // 39 words per column: odd, so column-parallel access is conflict free
 #define PP_U_BYTES (3 * PP_UH * PP_UW)
 #define PP_GHT_BYTES (3 * PP_GW * PP_GHT_STRIDE * 4)
 #define PP_G_BYTES (3 * PP_GH * PP_GW)
@@ -48,7 +48,8 @@ struct PPFrame {
     const uint8_t* raw;        // [in_h][in_w][3] raw camera frame
     const int32_t* m1;         // [n_cam][S][S] (sy << 16) | (sx & 0xffff): integer source coordinates of cv2's fixed-point map
     const uint16_t* m2;        // [n_cam][S][S] (fy << 5) | fx, the 1/32 px fractions
-    uint8_t* out;              // [S][S][3] processed frame
+    uint8_t* out;              // [S][S][3] processed frame, or null
+    uint8_t* gray;             // [S][S] what _find_dot's cvtColor(RGB2GRAY) makes of the processed frame, or null
     int in_w, in_h, S, rot, ay;
     int map_offset;            // cam * S * S: where this camera's map starts in m1 / m2
     int word_stores;           // out rows are 4-byte aligned (S % 4 == 0 and aligned base)
@@ -141,14 +142,23 @@ PP_HD int pp_squared_tap(const PPFrame& f, int y, int x, int& offset) {
 
 // ---- stage 1: cv.undistort = fixed-point bilinear remap (weights sum to 2^15 in OpenCV; the common factor
 // 32 is dropped here: (32 s + 2^14) >> 15 == (s + 2^9) >> 10), BORDER_CONSTANT 0
+PP_HD int pp_map_index(const PPFrame& f, int x0, int y0, int i, int mirror) {
+    const int ty = (int)((unsigned)i / (unsigned)PP_UW), tx = i - ty * PP_UW;
+    const int y = pp_reflect101(y0 - 6 + ty, f.S, mirror), x = pp_reflect101(x0 - 6 + tx, f.S, mirror);
+    return f.map_offset + y * f.S + x;                     // 32-bit index: n_cam * S * S < 2^31 is checked at set-up
+}
+
 PP_HD void pp_stage_undistort(const PPFrame& f, uint8_t* U, int x0, int y0, int tid, int nt) {
-    const int S = f.S, mirror = 2 * (S - 1);
-    for (int i = tid; i < PP_UH * PP_UW; i += nt) {
-        const int ty = i / PP_UW, tx = i - ty * PP_UW;
-        const int y = pp_reflect101(y0 - 6 + ty, S, mirror), x = pp_reflect101(x0 - 6 + tx, S, mirror);
-        const int mi = f.map_offset + y * S + x;          // 32-bit index: n_cam * S * S < 2^31 is checked at set-up
-        const int32_t m = f.m1[mi];
-        const int fr = f.m2[mi];
+    const int S = f.S, mirror = 2 * (S - 1), N = PP_UH * PP_UW;
+    // the map entry of the NEXT pixel is fetched before the current pixel's taps are, so the two dependent
+    // global round trips of a pixel (map -> taps) overlap with its neighbour's
+    int32_t m_next = 0;
+    int fr_next = 0;
+    if (tid < N) { const int mi = pp_map_index(f, x0, y0, tid, mirror); m_next = f.m1[mi]; fr_next = f.m2[mi]; }
+    for (int i = tid; i < N; i += nt) {
+        const int32_t m = m_next;
+        const int fr = fr_next;
+        if (i + nt < N) { const int mi = pp_map_index(f, x0, y0, i + nt, mirror); m_next = f.m1[mi]; fr_next = f.m2[mi]; }
         const int sx = (int16_t)(m & 0xffff), sy = m >> 16;
         const int fx = fr & 31, fy = (fr >> 5) & 31;
         const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy), w10 = (32 - fx) * fy, w11 = fx * fy;
@@ -169,8 +179,9 @@ PP_HD void pp_stage_undistort(const PPFrame& f, uint8_t* U, int x0, int y0, int 
                 v1 += p[1] * w00 + p[4] * w01 + q[1] * w10 + q[4] * w11;
                 v2 += p[2] * w00 + p[5] * w01 + q[2] * w10 + q[5] * w11;
             }
-        } else {
-            // the zero border, the feathered rows or the frame edge: tap by tap (rare, kept compact)
+        } else if ((unsigned)(ry + 9) < (unsigned)(f.in_h + 17)) {
+            // rows -9 .. in_h + 7: the feathered rows, the frame edge or the side border, tap by tap (rare, kept
+            // compact); anything further out is the zero padding of make_square and stays 0
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
@@ -197,7 +208,8 @@ PP_HD void pp_stage_blur_h(const uint8_t* U, uint32_t* GhT, int tid, int nt) {
     const uint32_t* Uw = reinterpret_cast<const uint32_t*>(U);
     const int RP = PP_UH / 2, NG = PP_GW / 4;
     for (int i = tid; i < 3 * RP * NG; i += nt) {
-        const int rp = i % RP, g = (i / RP) % NG, c = i / (RP * NG);
+        const unsigned ui = (unsigned)i, q1 = ui / (unsigned)RP, q2 = q1 / (unsigned)NG;
+        const int rp = (int)(ui - q1 * RP), g = (int)(q1 - q2 * NG), c = (int)q2;
         uint32_t o[2][4];
         PP_UNROLL
         for (int r = 0; r < 2; ++r) {
@@ -217,7 +229,8 @@ PP_HD void pp_stage_blur_h(const uint8_t* U, uint32_t* GhT, int tid, int nt) {
 PP_HD void pp_stage_blur_v(const uint32_t* GhT, uint8_t* G, int tid, int nt) {
     const int NQ = PP_GH / 4;
     for (int i = tid; i < 3 * NQ * PP_GW; i += nt) {
-        const int x = i % PP_GW, yq = (i / PP_GW) % NQ, c = i / (PP_GW * NQ);
+        const unsigned ui = (unsigned)i, q1 = ui / (unsigned)PP_GW, q2 = q1 / (unsigned)NQ;
+        const int x = (int)(ui - q1 * PP_GW), yq = (int)(q1 - q2 * NQ), c = (int)q2;
         const uint32_t* col = GhT + (c * PP_GW + x) * PP_GHT_STRIDE + 2 * yq;
         uint32_t w[6];
         PP_UNROLL
@@ -259,16 +272,28 @@ PP_HD void pp_stage_sharpen_store(const PPFrame& f, const uint8_t* G, int x0, in
             for (int j = 0; j < 4; ++j) a[c][j] = a[c][j] < 0 ? 0 : (a[c][j] > 255 ? 255 : a[c][j]);
         }
         // RGB -> BGR (helpers.py:82): byte order per pixel is channel 2, 1, 0
-        uint8_t* o = f.out + ((size_t)y * f.S + x) * 3;
-        if (f.word_stores) {
-            uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-            ow[0] = (uint32_t)a[2][0] | ((uint32_t)a[1][0] << 8) | ((uint32_t)a[0][0] << 16) | ((uint32_t)a[2][1] << 24);
-            ow[1] = (uint32_t)a[1][1] | ((uint32_t)a[0][1] << 8) | ((uint32_t)a[2][2] << 16) | ((uint32_t)a[1][2] << 24);
-            ow[2] = (uint32_t)a[0][2] | ((uint32_t)a[2][3] << 8) | ((uint32_t)a[1][3] << 16) | ((uint32_t)a[0][3] << 24);
-        } else {
-            for (int j = 0; j < 4 && x + j < f.S; ++j) {
-                o[3 * j + 0] = (uint8_t)a[2][j]; o[3 * j + 1] = (uint8_t)a[1][j]; o[3 * j + 2] = (uint8_t)a[0][j];
+        if (f.out) {
+            uint8_t* o = f.out + ((size_t)y * f.S + x) * 3;
+            if (f.word_stores) {
+                uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+                ow[0] = (uint32_t)a[2][0] | ((uint32_t)a[1][0] << 8) | ((uint32_t)a[0][0] << 16) | ((uint32_t)a[2][1] << 24);
+                ow[1] = (uint32_t)a[1][1] | ((uint32_t)a[0][1] << 8) | ((uint32_t)a[2][2] << 16) | ((uint32_t)a[1][2] << 24);
+                ow[2] = (uint32_t)a[0][2] | ((uint32_t)a[2][3] << 8) | ((uint32_t)a[1][3] << 16) | ((uint32_t)a[0][3] << 24);
+            } else {
+                for (int j = 0; j < 4 && x + j < f.S; ++j) {
+                    o[3 * j + 0] = (uint8_t)a[2][j]; o[3 * j + 1] = (uint8_t)a[1][j]; o[3 * j + 2] = (uint8_t)a[0][j];
+                }
             }
+        }
+        // S1 reads the processed frame through cv2's RGB2GRAY (helpers.py:144), 15-bit fixed point with byte 0
+        // as "R": emitting that plane here lets the marker pipeline read 1 byte per pixel instead of 3
+        if (f.gray) {
+            uint32_t gq[4];
+            PP_UNROLL
+            for (int j = 0; j < 4; ++j) gq[j] = (uint32_t)(a[2][j] * 9798 + a[1][j] * 19235 + a[0][j] * 3735 + 16384) >> 15;
+            uint8_t* o = f.gray + (size_t)y * f.S + x;
+            if (f.word_stores) *reinterpret_cast<uint32_t*>(o) = gq[0] | (gq[1] << 8) | (gq[2] << 16) | (gq[3] << 24);
+            else for (int j = 0; j < 4 && x + j < f.S; ++j) o[j] = (uint8_t)gq[j];
         }
     }
 }

@@ -9,9 +9,9 @@
 #include "../../low-cost-mocap_b200/csrc/preproc_tile.cuh"
 
 extern "C" void hc_preprocess(const uint8_t* raw, int in_w, int in_h, int S, int rot, const int16_t* m1, const uint16_t* m2,
-                              uint8_t* out, int word_stores, int n_threads) {
+                              uint8_t* out, uint8_t* gray, int word_stores, int n_threads) {
     PPFrame f;
-    f.raw = raw; f.m1 = reinterpret_cast<const int32_t*>(m1); f.m2 = m2; f.out = out;
+    f.raw = raw; f.m1 = reinterpret_cast<const int32_t*>(m1); f.m2 = m2; f.out = out; f.gray = gray;
     f.in_w = in_w; f.in_h = in_h; f.S = S; f.rot = rot; f.ay = (S - in_h) / 2; f.word_stores = word_stores; f.map_offset = 0;
     std::vector<uint32_t> smem(PP_SMEM_BYTES / 4 + 4);
     uint8_t* base = reinterpret_cast<uint8_t*>(smem.data());

@@ -123,9 +123,27 @@ def preprocess_rate():
         port.preprocess(frame, 0, dist, 0)
     cpu_ms = (time.perf_counter() - t0) / 20 * 1e3
     n_img = B * C
+    # raw frames -> tracks in one call (preprocess + S1-S3); noise frames are thresholded to nothing, so
+    # use dark frames with a few bright spots per camera
+    poses = [{"R": np.eye(3), "t": np.array([-0.4 * c, 0.0, 0.0])} for c in range(C)]
+    ctx.set_cameras([K] * C, poses)
+    dark = torch.randint(0, 25, (B, C, 240, 320, 3), dtype=torch.uint8, device="cuda")
+    yy, xx = torch.meshgrid(torch.arange(240, device="cuda"), torch.arange(320, device="cuda"), indexing="ij")
+    gen = np.random.default_rng(3)
+    for m in range(4):
+        X = np.array([gen.uniform(-0.3, 0.9), gen.uniform(-0.25, 0.25), gen.uniform(2.0, 3.0)])
+        for c in range(C):
+            pc = X + poses[c]["t"]
+            u, v = 320 * pc[0] / pc[2] + 160, 320 * pc[1] / pc[2] + 160 - 40
+            spot = (255 * torch.exp(-((yy - v) ** 2 + (xx - u) ** 2) / (2 * 2.0 ** 2))).to(torch.uint8)
+            dark[:, c] = torch.maximum(dark[:, c], spot[None, :, :, None])
+    raw_ms = timed(lambda: ctx.pipeline_raw(dark))
+    tracks = ctx.pipeline_raw(dark)
     return {"workload": "8000 raw 320x240x3 frames -> 320x320x3 (undistort + Gaussian 9x9 + 5x5 filter), one kernel",
             "ms": ms, "frames_per_s": n_img / ms * 1e3, "algorithmic_gbs": n_img * (240 * 320 * 3 + 320 * 320 * 3) / ms / 1e6,
-            "cpu_reference_ms_per_frame_1core": cpu_ms}
+            "cpu_reference_ms_per_frame_1core": cpu_ms,
+            "raw_to_tracks_ms": raw_ms, "raw_to_tracks_frame_sets_per_s": B / raw_ms * 1e3,
+            "raw_to_tracks_points_per_frame_set": float(tracks["n"].float().mean().item())}
 
 
 if __name__ == "__main__":

@@ -223,5 +223,10 @@ def test_preprocess_tile_stages_equal_cv2_chain_on_host(preproc_host, S, in_h, r
     for raw in frames:
         want = port.preprocess(raw, 0, dist, rot)
         got = np.full((S, S, 3), 7, dtype=np.uint8)
-        preproc_host.hc_preprocess(p(raw), S, in_h, S, rot, p(m1), p(m2), p(got), word_stores if S % 4 == 0 else 0, n_threads)
+        gray = np.full((S, S), 7, dtype=np.uint8)
+        preproc_host.hc_preprocess(p(raw), S, in_h, S, rot, p(m1), p(m2), p(got), p(gray), word_stores if S % 4 == 0 else 0, n_threads)
         assert np.array_equal(got, want), (np.argwhere(got != want)[:5], int((got != want).sum()))
+        assert np.array_equal(gray, cv2.cvtColor(want, cv2.COLOR_RGB2GRAY))      # what _find_dot thresholds (helpers.py:144)
+        only_gray = np.zeros((S, S), dtype=np.uint8)
+        preproc_host.hc_preprocess(p(raw), S, in_h, S, rot, p(m1), p(m2), None, p(only_gray), word_stores if S % 4 == 0 else 0, n_threads)
+        assert np.array_equal(only_gray, gray)

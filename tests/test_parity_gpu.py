@@ -711,6 +711,15 @@ def test_raw_frames_to_tracks_vs_oracle_chain(torch):
     assert total >= B
     out2 = ctx.pipeline_raw(torch.from_numpy(raw).cuda())              # without keeping the frames
     assert np.array_equal(out2["n"].cpu().numpy(), n)
+    assert np.array_equal(out2["obj"].cpu().numpy()[:, :n.max()], obj[:, :n.max()])
+    # other entry points grow and reuse the context's scratch memory; the preprocessing tables must survive that
+    # (they were once freed with it), and a much larger batch (several launch groups) must agree with the small one
+    big = 200000
+    ctx.triangulate(np.full((big, C, 2), 100.0), np.ones((big, C), dtype=np.uint8))
+    reps = 700
+    out3 = ctx.pipeline_raw(torch.from_numpy(np.tile(raw, (reps, 1, 1, 1, 1))).cuda())
+    assert np.array_equal(out3["n"].cpu().numpy(), np.tile(n, reps))
+    assert np.array_equal(out3["obj"].cpu().numpy()[:B, :n.max()], obj[:, :n.max()])
 
 
 @pytest.mark.parametrize("shape", [(320, 320, 3), (1024, 768, 1), (640, 480, 6), (48, 32, 2)])
