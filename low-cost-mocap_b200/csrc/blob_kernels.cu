@@ -55,33 +55,56 @@ k_threshold_segments_c1(const uint4* __restrict__ frames, long long n_seg, int s
 
 // 3-channel interleaved stream (the layout _find_dot receives).  grey as cv.cvtColor(RGB2GRAY)
 // computes it for 8-bit data: (c0*9798 + c1*19235 + c2*3735 + 16384) >> 15  (verified against cv2 4.13).
+// The weights sum to 2^15, so grey <= max(c0, c1, c2): a 16-pixel segment none of whose 48 bytes exceeds
+// the threshold cannot hold a pixel above it, and that is decided with the same packed byte test as the
+// 1-channel stream (39 integer ops per segment).  Only the rare segments that pass get the per-pixel
+// arithmetic, from a second (cache-resident) read, so the streaming loop stays small and keeps
+// 3 * UNROLL 128-bit loads in flight per thread.
+template <int UNROLL>
 __global__ void __launch_bounds__(256)
 k_threshold_segments_c3(const uint4* __restrict__ frames, long long n_seg, int seg_per_image,
-                        int max_segments, int threshold, uint32_t* __restrict__ seg_count,
+                        int max_segments, int threshold, ThreshConst tc, uint32_t* __restrict__ seg_count,
                         uint32_t* __restrict__ seg_list) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_seg; s += stride) {
-        uint32_t w[12];
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_seg; s += stride * UNROLL) {
+        uint4 v[UNROLL][3];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const uint4 v = ldg_stream(frames + s * 3 + q);
-            w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long si = s + stride * u;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) v[u][q] = (si < n_seg) ? ldg_stream(frames + si * 3 + q) : make_uint4(0, 0, 0, 0);
         }
-        uint32_t any = 0;
+        uint32_t todo = 0;
 #pragma unroll
-        for (int q = 0; q < 12; ++q) any |= w[q];
-        if (any == 0) continue;
-        uint32_t m = 0;
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-            const int o = 3 * p;
-            const uint32_t c0 = (w[o >> 2] >> ((o & 3) * 8)) & 0xffu;
-            const uint32_t c1 = (w[(o + 1) >> 2] >> (((o + 1) & 3) * 8)) & 0xffu;
-            const uint32_t c2 = (w[(o + 2) >> 2] >> (((o + 2) & 3) * 8)) & 0xffu;
-            const int grey = (int)((c0 * 9798u + c1 * 19235u + c2 * 3735u + 16384u) >> 15);
-            m |= (grey > threshold ? 1u : 0u) << p;
+        for (int u = 0; u < UNROLL; ++u) {
+            bool hit;
+            if (tc.use_and) hit = any_above<true>(v[u][0], tc) || any_above<true>(v[u][1], tc) || any_above<true>(v[u][2], tc);
+            else hit = any_above<false>(v[u][0], tc) || any_above<false>(v[u][1], tc) || any_above<false>(v[u][2], tc);
+            todo |= (hit ? 1u : 0u) << u;
         }
-        if (m) append_segment(seg_count, seg_list, max_segments, s, seg_per_image, m);
+        while (todo) {
+            const int u = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const long long si = s + stride * u;
+            if (si >= n_seg) break;
+            uint32_t w[12];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const uint4 x = __ldg(frames + si * 3 + q);
+                w[4 * q + 0] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
+            }
+            uint32_t m = 0;
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const int o = 3 * p;
+                const uint32_t c0 = (w[o >> 2] >> ((o & 3) * 8)) & 0xffu;
+                const uint32_t c1 = (w[(o + 1) >> 2] >> (((o + 1) & 3) * 8)) & 0xffu;
+                const uint32_t c2 = (w[(o + 2) >> 2] >> (((o + 2) & 3) * 8)) & 0xffu;
+                const int grey = (int)((c0 * 9798u + c1 * 19235u + c2 * 3735u + 16384u) >> 15);
+                m |= (grey > threshold ? 1u : 0u) << p;
+            }
+            if (m) append_segment(seg_count, seg_list, max_segments, si, seg_per_image, m);
+        }
     }
 }
 
@@ -175,27 +198,27 @@ int launch_detect(mocap_ctx* ctx, const uint8_t* frames, int n_images, int chann
         CUDA_TRY(ctx, cudaEventRecord(ctx->tim_ev[2 * ctx->tim_used], ctx->stream));
     }
     const int threads = 256;
+    ThreshConst tc;
+    if (threshold < 0) { tc.addc = 0x80808080u; tc.use_and = 0; }            // everything passes
+    else if (threshold >= 255) { tc.addc = 0; tc.use_and = 1; }              // nothing passes
+    else {
+        const uint32_t T1 = (uint32_t)threshold + 1u;
+        tc.use_and = T1 > 128 ? 1u : 0u;
+        tc.addc = (T1 > 128 ? 256u - T1 : 128u - T1) * 0x01010101u;
+    }
+    const long long cap = (long long)ctx->num_sms * 8;      // 8 CTAs of 256 threads fill an SM
     if (channels == 1) {
         constexpr int UNROLL = 8;
-        ThreshConst tc;
-        if (threshold < 0) { tc.addc = 0x80808080u; tc.use_and = 0; }            // everything passes
-        else if (threshold >= 255) { tc.addc = 0; tc.use_and = 1; }              // nothing passes
-        else {
-            const uint32_t T1 = (uint32_t)threshold + 1u;
-            tc.use_and = T1 > 128 ? 1u : 0u;
-            tc.addc = (T1 > 128 ? 256u - T1 : 128u - T1) * 0x01010101u;
-        }
         long long want = (n_seg + (long long)threads * UNROLL - 1) / ((long long)threads * UNROLL);
-        const long long cap = (long long)ctx->num_sms * 8;      // 8 CTAs of 256 threads fill an SM
         const int grid = (int)(want < cap ? want : cap);
         k_threshold_segments_c1<UNROLL><<<grid, threads, 0, ctx->stream>>>(
             reinterpret_cast<const uint4*>(frames), n_seg, seg_per_image, E, tc, ctx->d_seg_count, ctx->d_seg_list);
     } else {
-        long long want = (n_seg + threads - 1) / threads;
-        const long long cap = (long long)ctx->num_sms * 8;
+        constexpr int UNROLL = 2;
+        long long want = (n_seg + (long long)threads * UNROLL - 1) / ((long long)threads * UNROLL);
         const int grid = (int)(want < cap ? want : cap);
-        k_threshold_segments_c3<<<grid, threads, 0, ctx->stream>>>(
-            reinterpret_cast<const uint4*>(frames), n_seg, seg_per_image, E, threshold, ctx->d_seg_count, ctx->d_seg_list);
+        k_threshold_segments_c3<UNROLL><<<grid, threads, 0, ctx->stream>>>(
+            reinterpret_cast<const uint4*>(frames), n_seg, seg_per_image, E, threshold, tc, ctx->d_seg_count, ctx->d_seg_list);
     }
     CUDA_TRY(ctx, cudaGetLastError());
     if (ctx->timing_on) {

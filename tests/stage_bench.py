@@ -58,6 +58,26 @@ def config3_pipeline():
             "pipeline": os.environ.get("MOCAP_PIPELINE", "fused")}
 
 
+def colour_pipeline():
+    """The layout _find_dot actually receives (helpers.py:143-145): 3 interleaved channels per pixel.  Config-2
+    shape, every channel carrying the synthetic grey frame, compared with the 1-channel run of the same frames."""
+    C, M, P, B = 4, 4, 64, 2000
+    frames, truth, poses, K = synth.make_frame_pool(C, M, P, seed=1)
+    ctx = pkg.MocapContext(C, 640, 480, max_roots=16)
+    ctx.set_cameras([K] * C, poses)
+    pool = torch.from_numpy(frames).cuda()
+    grey = pool[torch.arange(B, device="cuda") % P].contiguous()
+    colour = grey[..., None].expand(-1, -1, -1, -1, 3).contiguous()          # 7.4 GB
+    out1, out3 = ctx.alloc_tracks(B), ctx.alloc_tracks(B)
+    ctx.pipeline(grey, out=out1)
+    ms = timed(lambda: ctx.pipeline(colour, out=out3))
+    valid = torch.arange(out1["obj"].shape[1], device="cuda")[None, :] < out1["n"][:, None]
+    same = bool(torch.equal(out1["n"], out3["n"]) and torch.equal(out1["obj"][valid], out3["obj"][valid]))
+    return {"workload": "4 cameras, 4 markers, 2000 frame-sets of 640x480x3 interleaved (7.4 GB resident), three-kernel path",
+            "ms_per_batch": ms, "frame_sets_per_s": B / ms * 1e3, "hbm_gbs": B * C * 921600 / ms / 1e6,
+            "equals_one_channel_run": same}
+
+
 def dlt_rate():
     C, F = 8, 1_000_000
     obs_obj, poses, K, pts = synth.make_tracks(C, 2000, seed=3)
@@ -150,10 +170,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "config3":      # for ncu: just the 8-camera pipeline
         print(json.dumps(config3_pipeline()))
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "colour":
+        print(json.dumps(colour_pipeline()))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
         print(json.dumps(preprocess_rate()))
         sys.exit(0)
-    out = {"preprocess": preprocess_rate(),"config3_pipeline": config3_pipeline(), "dlt": dlt_rate(),
+    out = {"preprocess": preprocess_rate(), "colour_pipeline": colour_pipeline(),"config3_pipeline": config3_pipeline(), "dlt": dlt_rate(),
            "ba_config3_batch": ba_case(8, 16000, "config 3 per-batch BA: 8 cameras, 1000 frames x 16 markers = 16000 tracked points"),
            "ba_config5": ba_case(16, 6400, "config 5 cold start: 16 cameras, 64 markers x 100 frames = 6400 tracked points")}
     print(json.dumps(out, indent=1))

@@ -106,6 +106,27 @@ def test_threshold_is_strictly_greater(torch, threshold):
     assert (n == min(expect, 64)) and ((flags & 2) != 0) == (expect > 64)
 
 
+@pytest.mark.parametrize("threshold", [0, 51, 127, 128, 129, 254, 255])
+def test_three_channel_threshold_regimes(torch, threshold):
+    """3-channel stream: the packed "no byte above the threshold" skip must never drop a segment whose grey
+    value (cv2's fixed-point RGB2GRAY) passes, in both compare regimes; isolated 2x2 squares of random colours
+    plus colours whose grey value sits right at the threshold."""
+    import cv2
+    rng = np.random.default_rng(threshold + 7)
+    img = np.zeros((480, 640, 3), np.uint8)
+    cols = rng.integers(0, 256, size=(60, 3), dtype=np.uint8)
+    t = min(max(threshold, 1), 254)
+    cols[:8] = np.array([[255, 0, 0], [0, 255, 0], [0, 0, 255], [t + 1, t, t], [t, t + 1, t], [t, t, t + 1], [t, t, t], [t + 1] * 3], dtype=np.uint8)
+    for v in range(60):
+        y, x = 6 + 12 * (v // 20), 6 + 12 * (v % 20)
+        img[y:y + 2, x:x + 2] = cols[v]
+    grey = cv2.cvtColor(img, cv2.COLOR_RGB2GRAY)
+    expect = int(sum(grey[6 + 12 * (v // 20), 6 + 12 * (v % 20)] > threshold for v in range(60)))
+    ctx = _ctx(1, max_blobs=64, max_segments=1024)
+    d = ctx.detect(torch.from_numpy(img[None]).cuda(), threshold=threshold)
+    assert int(d["n"][0]) == expect and int(d["flags"][0]) == 0
+
+
 def test_detect_edge_cases(torch):
     ctx = _ctx(1, max_blobs=8, max_segments=64)
     imgs = np.zeros((6, 480, 640), np.uint8)
