@@ -239,18 +239,33 @@ def run_gpu_arm(args):
     owned = torch.from_numpy(sharding.shard_indices(BATCH * world, rank, world)).to(dev)
     batch = pool_dev[owned % POOL].contiguous()                   # [BATCH, C, H, W] uint8, 12.3 GB
     del pool_dev
-    # the matcher writes straight into the all-gather send buffer (one flat allocation)
-    tracks = sharding.TrackBuffer(BATCH, MAX_ROOTS, dev)
-    out = tracks.views
+    # the matcher writes straight into the all-gather send buffer (one flat allocation); two buffers in turn,
+    # so that on the multi-GPU path batch k's tracks travel while batch k+1 is being processed
+    track_bufs = [sharding.TrackBuffer(BATCH, MAX_ROOTS, dev) for _ in range(2 if world > 1 else 1)]
+    pending = [None] * len(track_bufs)
+    out = track_bufs[0].views
     bytes_per_step = batch.numel()
+    step_no = [0]
 
     def step():
-        ctx.pipeline(batch, out=out)
+        k = step_no[0] % len(track_bufs)
+        step_no[0] += 1
+        if pending[k] is not None:
+            pending[k].wait()                # this buffer's previous all-gather has read it
+            pending[k] = None
+        ctx.pipeline(batch, out=track_bufs[k].views)
         if world > 1:
-            return tracks.all_gather()       # ONE NCCL all-gather per batch; consumers read views
-        return None
+            # ONE NCCL all-gather per batch, enqueued behind the pipeline kernel; consumers read views
+            _, pending[k] = track_bufs[k].all_gather(async_op=True)
+
+    def drain():
+        for k, w in enumerate(pending):
+            if w is not None:
+                w.wait()
+                pending[k] = None
 
     def sync_all():
+        drain()
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -273,6 +288,7 @@ def run_gpu_arm(args):
     e0.record()
     for _ in range(args.steps):
         step()
+    drain()                                  # the stream now waits for the last all-gathers: they are inside the timed region
     e1.record()
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

@@ -91,13 +91,18 @@ class TrackBuffer:
                 "n": flat[o[2]: o[2] + self.sizes[2]].view(torch.int32),
                 "flags": flat[o[3]: o[3] + self.sizes[3]].view(torch.int32)}
 
-    def all_gather(self, group=None):
+    def all_gather(self, group=None, async_op=False):
         """ONE collective over the raw bytes; returns per-rank views [world] of dicts like ``views``.
-        Global frame-set f lives at rank f % world, local index f // world (round-robin ownership)."""
+        Global frame-set f lives at rank f % world, local index f // world (round-robin ownership).
+
+        With ``async_op=True`` returns ``(views, work)``: the collective is only enqueued (after the work
+        already on the current stream), so the next batch's kernels can run while the tracks travel; call
+        ``work.wait()`` before reading the views or writing this buffer again (use two buffers in turn)."""
         import torch
         import torch.distributed as dist
         world = dist.get_world_size(group)
         if self.gathered is None or self.gathered.shape[0] != world:
             self.gathered = torch.empty((world, self.nbytes), dtype=torch.uint8, device=self.flat.device)
-        dist.all_gather_into_tensor(self.gathered.view(-1), self.flat, group=group)
-        return [self._views(self.gathered[r]) for r in range(world)]
+        work = dist.all_gather_into_tensor(self.gathered.view(-1), self.flat, group=group, async_op=async_op)
+        views = [self._views(self.gathered[r]) for r in range(world)]
+        return (views, work) if async_op else views

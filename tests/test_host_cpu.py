@@ -88,6 +88,20 @@ for n_total in (9, 10):
         for f in range(n_total):
             v = per_rank[f % world]
             assert torch.equal(v["obj"][f // world], obj[f]) and v["n"][f // world] == n[f], "flat gather mismatch"
+        # pipelined form (bench.py at N > 1): two buffers in turn, the collective only enqueued, waited for
+        # before its buffer is written again
+        bufs = [sharding.TrackBuffer(n_total // world, R, "cpu") for _ in range(2)]
+        pending = [None, None]
+        for step in range(5):
+            k = step % 2
+            if pending[k] is not None:
+                views, work = pending[k]
+                work.wait()
+                assert torch.equal(views[1 - rank]["obj"][0], obj[1 - rank] + (step - 2)), "pipelined gather mismatch"
+            bufs[k].views["obj"].copy_(obj[mine] + step)
+            pending[k] = bufs[k].all_gather(async_op=True)
+        for k in range(2):
+            pending[k][1].wait()
 dist.destroy_process_group()
 print("OK", rank)
 """
