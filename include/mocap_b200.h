@@ -149,9 +149,11 @@ MOCAP_API int mocap_set_preprocess(mocap_ctx* ctx, int in_width, int in_height, 
  * n_images = n_frame_sets * n_cam (camera index = image index mod n_cam). */
 MOCAP_API int mocap_preprocess_dev(mocap_ctx* ctx, const uint8_t* raw_frames, int n_images, uint8_t* out_frames);
 /* The whole per-frame body of Cameras._camera_read (helpers.py:70-103) for n_frame_sets frame-sets of RAW
- * camera frames: preprocessing (as mocap_preprocess_dev) -> S1 on the processed 3-channel frames ->
- * S2+S3.  processed (uint8 [n_images][S][S][3], the frames the reference goes on to JPEG-encode) may be
- * NULL when the caller does not display them.  DEVICE pointers. */
+ * camera frames: preprocessing (as mocap_preprocess_dev) -> S1 -> S2+S3.  The preprocessing kernel also
+ * emits the grey plane _find_dot's cvtColor(RGB2GRAY) would derive from the processed frame
+ * (helpers.py:144), so S1-S3 read 1 byte per pixel; results are those of S1 on the 3-channel frames.
+ * processed (uint8 [n_images][S][S][3], the frames the reference goes on to JPEG-encode) may be NULL when
+ * the caller does not display them (then they are never written).  DEVICE pointers. */
 MOCAP_API int mocap_pipeline_raw_dev(mocap_ctx* ctx, const uint8_t* raw_frames, int n_frame_sets, int threshold,
                            uint8_t* processed, double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
 /* The fixed-point undistortion map of one camera as built by mocap_set_preprocess (the tables
