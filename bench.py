@@ -130,24 +130,30 @@ def cpu_pass(pool_obj, frames, n_sets):
     return time.perf_counter() - t0, sum(got)
 
 
-def check_against_oracle(frames, poses, K, out, n_check=8):
-    """3D-point distance to the reference (oracle port) on the first frame-sets of the batch the timed steps
-    processed (rank 0's shard starts with pool frame-sets 0, world, 2*world, ...; at N = 1 these are 0..n-1)."""
-    from oracle.ref_port import RefPort
-    port = RefPort([K] * len(poses))
-    n = out["n"][:n_check].cpu().numpy()
-    obj = out["obj"][:n_check].cpu().numpy()
-    worst, same_count, points = 0.0, True, 0
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+def oracle_tracks(frames, world, n_check=8):
+    """Part of the cpu_baseline leg: the oracle port's 3D points for the first frame-sets rank 0 owns (global
+    frame-sets 0, world, 2*world, ... of the round-robin stream), kept to check the GPU results against."""
+    port, poses = _W["port"], _W["poses"]
+    ref = []
     for b in range(n_check):
         fs = frames[(b * world) % len(frames)]
         pts = [port.find_dot(np.repeat(img[:, :, None], 3, axis=2)) for img in fs]
         e, o, _ = port.match_and_triangulate(pts, poses)
-        same_count = same_count and (len(e) == int(n[b]))
-        if len(e) and len(e) == int(n[b]):
-            worst = max(worst, float(np.abs(obj[b, :len(e)] - np.asarray(o, dtype=np.float64)).max()))
-            points += len(e)
-    return {"frame_sets": n_check, "points": points, "point_counts_equal": bool(same_count),
+        ref.append(np.asarray(o, dtype=np.float64).reshape(-1, 3))
+    return ref
+
+
+def compare_with_oracle(ref, out):
+    """3D-point distance between the GPU results of a timed step and the cpu_baseline leg's oracle output."""
+    n = out["n"][:len(ref)].cpu().numpy()
+    obj = out["obj"][:len(ref)].cpu().numpy()
+    worst, same_count, points = 0.0, True, 0
+    for b, o in enumerate(ref):
+        same_count = same_count and (len(o) == int(n[b]))
+        if len(o) and len(o) == int(n[b]):
+            worst = max(worst, float(np.abs(obj[b, :len(o)] - o).max()))
+            points += len(o)
+    return {"frame_sets": len(ref), "points": points, "point_counts_equal": bool(same_count),
             "max_abs_3d_difference": worst, "tolerance": 1e-7}
 
 
@@ -224,7 +230,8 @@ def run_gpu_arm(args):
         while time.perf_counter() - t0 < 3.0:
             _cpu_one(n_single)
             n_single += 1
-        cpu_res = (cores, sample, t_cpu, n_single / (time.perf_counter() - t0))
+        single_core = n_single / (time.perf_counter() - t0)
+        cpu_res = (cores, sample, t_cpu, single_core, oracle_tracks(frames, world))
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -343,8 +350,8 @@ def run_gpu_arm(args):
         # step bytes * steps / launches (one launch per step for the fused kernel, three for the split pipeline)
         alg_bytes = bytes_per_step * args.steps / kern_n if kern_n else None
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
-        cores, sample, t_cpu, single_core = cpu_res
-        parity = check_against_oracle(frames, poses, K, out)
+        cores, sample, t_cpu, single_core, ref_tracks = cpu_res
+        parity = compare_with_oracle(ref_tracks, out)
         gpu_points = int(out["n"][:1].sum().item())
         line = {
             "metric": f"mocap frame-sets/s ({N_CAM}-cam 640x480 synthetic, blob+epipolar+DLT)",
