@@ -95,8 +95,10 @@ int mocap_create(mocap_ctx** out, const mocap_config* cfg) {
         for (int k = 0; k < 2 * 64; ++k)
             if (cudaEventCreate(&ctx->tim_ev[k]) != cudaSuccess) { st = MOCAP_ECUDA; break; }
         if (st) break;
-        for (int k = 0; k < 2; ++k)
+        for (int k = 0; k < 2; ++k) {
             if (cudaEventCreateWithFlags(&ctx->stage_free[k], cudaEventDisableTiming) != cudaSuccess) { st = MOCAP_ECUDA; break; }
+            if (cudaEventCreateWithFlags(&ctx->copied[k], cudaEventDisableTiming) != cudaSuccess) { st = MOCAP_ECUDA; break; }
+        }
         if (st) break;
         if ((st = blob_kernels_init(ctx)) != MOCAP_OK) break;
         if ((st = match_kernels_init(ctx)) != MOCAP_OK) break;
@@ -130,6 +132,7 @@ void mocap_destroy(mocap_ctx* ctx) {
     if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
     for (int k = 0; k < 2 * 64; ++k) if (ctx->tim_ev[k]) cudaEventDestroy(ctx->tim_ev[k]);
     for (int k = 0; k < 2; ++k) if (ctx->stage_free[k]) cudaEventDestroy(ctx->stage_free[k]);
+    for (int k = 0; k < 2; ++k) if (ctx->copied[k]) cudaEventDestroy(ctx->copied[k]);
     delete ctx;
 }
 
@@ -334,9 +337,7 @@ int mocap_pipeline_host(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets,
     if (st) return st;
     st = ensure_images(ctx, chunk * C);
     if (st) return st;
-    cudaEvent_t copied[2];
-    CUDA_TRY(ctx, cudaEventCreateWithFlags(&copied[0], cudaEventDisableTiming));
-    CUDA_TRY(ctx, cudaEventCreateWithFlags(&copied[1], cudaEventDisableTiming));
+    cudaEvent_t* copied = ctx->copied;
     // the copies must not start before earlier work on the caller's stream has finished with the staging buffers
     CUDA_TRY(ctx, cudaEventRecord(copied[0], ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, copied[0], 0));
@@ -364,9 +365,6 @@ int mocap_pipeline_host(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets,
                           ctx->d_nobj + s0, ctx->d_setflags + s0, nullptr);
         if (st) break;
     }
-    cudaEventDestroy(copied[1]);
-    cudaEvent_t copied0 = copied[0];
-    cudaEventDestroy(copied0);
     if (st) return st;
     const size_t n = (size_t)n_frame_sets;
     CUDA_TRY(ctx, cudaMemcpyAsync(obj, ctx->d_obj, n * RM * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -55,7 +55,7 @@ struct mocap_ctx {
     // host-path staging
     uint8_t*  d_stage[2];
     size_t    stage_bytes;
-    cudaEvent_t stage_free[2];
+    cudaEvent_t stage_free[2]; cudaEvent_t copied[2];   // per staging buffer: its kernel has finished / its copy has landed
     double*   d_obj; double* d_err; int32_t* d_nobj; int32_t* d_setflags;
     int       cap_sets;
     // generic scratch for the *_host triangulation / BA entry points
