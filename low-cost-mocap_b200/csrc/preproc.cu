@@ -21,9 +21,11 @@
 // undistortion map per camera: m1 int16 [S][S][2] integer source coordinates (x, y), read by the kernel as
 //                            one 32-bit word per pixel;  m2 uint16 [S][S]   (fy << 5) | fx, the 1/32 px fractions
 //
-// One CTA = one 64x64 output tile (preproc_tile.cuh): four stages separated by barriers, 48 KB of shared
-// memory and 46 registers, so 4 CTAs are resident per SM and one CTA's gather overlaps its neighbours'
-// filter stages.  (A 64x32 tile keeps 7 CTAs resident but undistorts 16 % more apron pixels: 8 % slower.)
+// One CTA = one 64x64 output tile (preproc_tile.cuh): gather, then the two blur passes channel by channel
+// (the transposed Q8.8 plane holds one channel), then the 5x5 filter; stages separated by barriers.  28 KB of
+// shared memory and 32 registers, so 8 CTAs (all 64 warps) are resident per SM and one CTA's gather overlaps
+// its neighbours' filter stages.  (All three channels at once: 48 KB, 4 CTAs/SM, 8 % slower.  A 64x32 tile
+// undistorts 16 % more apron pixels: 8 % slower.)
 __global__ void __launch_bounds__(256)
 k_preprocess(const uint8_t* __restrict__ raw_frames, int C, int in_w, int in_h, int S, const int* __restrict__ rotation,
              const int32_t* __restrict__ m1, const uint16_t* __restrict__ m2, uint8_t* __restrict__ out, uint8_t* __restrict__ gray,
@@ -48,10 +50,12 @@ k_preprocess(const uint8_t* __restrict__ raw_frames, int C, int in_w, int in_h, 
     const int nt = 256;
     pp_stage_undistort(f, U, x0, y0, tid, nt);
     __syncthreads();
-    pp_stage_blur_h(U, GhT, tid, nt);
-    __syncthreads();
-    pp_stage_blur_v(GhT, G, tid, nt);
-    __syncthreads();
+    for (int c0 = 0; c0 < 3; c0 += PP_GHT_CH) {
+        pp_stage_blur_h(U, GhT, c0, tid, nt);
+        __syncthreads();
+        pp_stage_blur_v(GhT, G, c0, tid, nt);
+        __syncthreads();
+    }
     pp_stage_sharpen_store(f, G, x0, y0, tid, nt);
 }
 

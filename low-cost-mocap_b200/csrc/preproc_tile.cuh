@@ -11,9 +11,11 @@
 //                                    applied here, by undistorting the mirrored coordinate, so no later
 //                                    stage needs border logic: the blur of a mirrored image is the mirror
 //                                    of the blur because the kernel is symmetric)
-//   GhT  [3][PP_GW][PP_GHT_STRIDE]   u32  horizontal 9-tap pass, Q8.8 in u16, TRANSPOSED and packed as row
+//   GhT  [PP_GHT_CH][PP_GW][PP_GHT_STRIDE]   u32  horizontal 9-tap pass, Q8.8 in u16, TRANSPOSED and packed as row
 //                                    pairs so the vertical pass is a 2-way 16x8 dot product per word
-//   G    [3][PP_GH][PP_GW]      u8   blurred pixels of the tile + 2 px apron (in U's storage)
+//   G    [3][PP_GH][PP_GW]      u8   blurred pixels of the tile + 2 px apron (in U's storage: plane c of G ends
+//                                    before plane c of U does, so writing G channel by channel, each after its
+//                                    horizontal pass has consumed U, never touches a U plane still to be read)
 // OpenCV's 8-bit GaussianBlur accumulates exactly (kernel sums to 256, Q8.8 after one pass, Q8.16 after
 // two, one rounding at the end), so the result is (sum_yx ky kx U + 2^15) >> 16 in any order.
 #pragma once
@@ -38,7 +40,10 @@
 #define PP_GH (PP_TY + 4)                  // 68 = 17 groups of 4
 #define PP_GHT_STRIDE (PP_UH / 2 + 1)      // 39 words per column: odd, so column-parallel access is conflict free
 #define PP_U_BYTES (3 * PP_UH * PP_UW)
-#define PP_GHT_BYTES (3 * PP_GW * PP_GHT_STRIDE * 4)
+#ifndef PP_GHT_CH
+#define PP_GHT_CH 1                        // channel planes GhT holds (1 or 3): the two blur passes run per group of
+#endif                                     // PP_GHT_CH channels; 1 keeps the tile at 28 KB so that 5 CTAs are resident
+#define PP_GHT_BYTES (PP_GHT_CH * PP_GW * PP_GHT_STRIDE * 4)
 #define PP_G_BYTES (3 * PP_GH * PP_GW)
 // G reuses U's bytes: U is dead once the horizontal pass has run, G is born in the vertical pass
 #define PP_SMEM_BYTES (PP_U_BYTES + PP_GHT_BYTES)
@@ -204,16 +209,17 @@ PP_HD void pp_stage_undistort(const PPFrame& f, uint8_t* U, int x0, int y0, int 
 
 // ---- stage 2a: horizontal 9 taps.  One item = 4 outputs x 2 rows of one channel: 3 words per row in,
 // 3 four-way dot products per output, 4 row-pair words out.
-PP_HD void pp_stage_blur_h(const uint8_t* U, uint32_t* GhT, int tid, int nt) {
+// Channels c0 .. c0 + PP_GHT_CH - 1 of U -> GhT (which holds PP_GHT_CH channel planes).
+PP_HD void pp_stage_blur_h(const uint8_t* U, uint32_t* GhT, int c0, int tid, int nt) {
     const uint32_t* Uw = reinterpret_cast<const uint32_t*>(U);
     const int RP = PP_UH / 2, NG = PP_GW / 4;
-    for (int i = tid; i < 3 * RP * NG; i += nt) {
+    for (int i = tid; i < PP_GHT_CH * RP * NG; i += nt) {
         const unsigned ui = (unsigned)i, q1 = ui / (unsigned)RP, q2 = q1 / (unsigned)NG;
         const int rp = (int)(ui - q1 * RP), g = (int)(q1 - q2 * NG), c = (int)q2;
         uint32_t o[2][4];
         PP_UNROLL
         for (int r = 0; r < 2; ++r) {
-            const uint32_t* row = Uw + (c * PP_UH + 2 * rp + r) * (PP_UW / 4) + g;
+            const uint32_t* row = Uw + ((c0 + c) * PP_UH + 2 * rp + r) * (PP_UW / 4) + g;
             const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
             PP_UNROLL
             for (int j = 0; j < 4; ++j)
@@ -226,9 +232,9 @@ PP_HD void pp_stage_blur_h(const uint8_t* U, uint32_t* GhT, int tid, int nt) {
 
 // ---- stage 2b: vertical 9 taps + the single rounding.  One item = 4 output rows of one column of one
 // channel: 6 row-pair words in, 5 two-way dot products per output.
-PP_HD void pp_stage_blur_v(const uint32_t* GhT, uint8_t* G, int tid, int nt) {
+PP_HD void pp_stage_blur_v(const uint32_t* GhT, uint8_t* G, int c0, int tid, int nt) {
     const int NQ = PP_GH / 4;
-    for (int i = tid; i < 3 * NQ * PP_GW; i += nt) {
+    for (int i = tid; i < PP_GHT_CH * NQ * PP_GW; i += nt) {
         const unsigned ui = (unsigned)i, q1 = ui / (unsigned)PP_GW, q2 = q1 / (unsigned)NQ;
         const int x = (int)(ui - q1 * PP_GW), yq = (int)(q1 - q2 * NQ), c = (int)q2;
         const uint32_t* col = GhT + (c * PP_GW + x) * PP_GHT_STRIDE + 2 * yq;
@@ -241,7 +247,7 @@ PP_HD void pp_stage_blur_v(const uint32_t* GhT, uint8_t* G, int tid, int nt) {
             PP_UNROLL
             for (int m = 0; m < 6; ++m)
                 if (pp_gauss_word2(j, m) != 0u) acc = pp_dp2a_lo(w[m], pp_gauss_word2(j, m), acc);
-            G[(c * PP_GH + 4 * yq + j) * PP_GW + x] = (uint8_t)(acc >> 16);
+            G[((c0 + c) * PP_GH + 4 * yq + j) * PP_GW + x] = (uint8_t)(acc >> 16);
         }
     }
 }

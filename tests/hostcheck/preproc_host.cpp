@@ -22,8 +22,10 @@ extern "C" void hc_preprocess(const uint8_t* raw, int in_w, int in_h, int S, int
         for (int x0 = 0; x0 < S; x0 += PP_TX) {
             memset(base, 0xA5, PP_SMEM_BYTES);                 // stale shared memory must not matter
             for (int t = 0; t < n_threads; ++t) pp_stage_undistort(f, U, x0, y0, t, n_threads);
-            for (int t = 0; t < n_threads; ++t) pp_stage_blur_h(U, GhT, t, n_threads);
-            for (int t = 0; t < n_threads; ++t) pp_stage_blur_v(GhT, G, t, n_threads);
+            for (int c0 = 0; c0 < 3; c0 += PP_GHT_CH) {
+                for (int t = 0; t < n_threads; ++t) pp_stage_blur_h(U, GhT, c0, t, n_threads);
+                for (int t = 0; t < n_threads; ++t) pp_stage_blur_v(GhT, G, c0, t, n_threads);
+            }
             for (int t = 0; t < n_threads; ++t) pp_stage_sharpen_store(f, G, x0, y0, t, n_threads);
         }
 }
