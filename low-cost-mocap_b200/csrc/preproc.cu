@@ -21,26 +21,35 @@
 // undistortion map per camera: m1 int16 [S][S][2] integer source coordinates (x, y), read by the kernel as
 //                            one 32-bit word per pixel;  m2 uint16 [S][S]   (fy << 5) | fx, the 1/32 px fractions
 //
-// One CTA = one 64x64 output tile (preproc_tile.cuh): gather, then the two blur passes channel by channel
-// (the transposed Q8.8 plane holds one channel), then the 5x5 filter; stages separated by barriers.  28 KB of
-// shared memory and 32 registers, so 8 CTAs (all 64 warps) are resident per SM and one CTA's gather overlaps
-// its neighbours' filter stages.  (All three channels at once: 48 KB, 4 CTAs/SM, 8 % slower.  A 64x32 tile
-// undistorts 16 % more apron pixels: 8 % slower.)
+// One CTA = one 64x64 output tile (preproc_tile.cuh) of TWO consecutive frames of one camera: the gather decodes
+// the camera's map once per pixel and applies it to both frames; then, frame by frame, the two blur passes
+// channel by channel (the transposed Q8.8 plane holds one channel) and the 5x5 filter; stages separated by
+// barriers.  45 KB of shared memory and 42 registers: 5 CTAs resident per SM, so one CTA's gather overlaps its
+// neighbours' filter stages.  Measured alternatives (8000 frames 320x240x3): one frame per CTA, 28 KB, 8 CTAs:
+// -9 %; blur of all three channels at once, 48 KB, 4 CTAs: -14 %; 64x32 tiles with 2 / 3 / 4 frames: -12 / -8 / -16 %.
+// blockIdx.z = frame group * C + camera; frame k of the group is image ((group * PP_F + k) * C + camera): the
+// PP_F frames a CTA handles belong to ONE camera, so the gather decodes that camera's map once per pixel.
 __global__ void __launch_bounds__(256)
-k_preprocess(const uint8_t* __restrict__ raw_frames, int C, int in_w, int in_h, int S, const int* __restrict__ rotation,
+k_preprocess(const uint8_t* __restrict__ raw_frames, int n_images, int C, int in_w, int in_h, int S, const int* __restrict__ rotation,
              const int32_t* __restrict__ m1, const uint16_t* __restrict__ m2, uint8_t* __restrict__ out, uint8_t* __restrict__ gray,
              int word_stores) {
     __shared__ __align__(16) uint8_t smem[PP_SMEM_BYTES];
-    uint8_t* U = smem;
-    uint32_t* GhT = reinterpret_cast<uint32_t*>(smem + PP_U_BYTES);
-    uint8_t* G = smem;                                  // over U (dead after the horizontal pass)
-    const int img = blockIdx.z, cam = img % C;
+    uint8_t* U = smem;                                                  // PP_F frames; G of a frame reuses its U
+    uint32_t* GhT = reinterpret_cast<uint32_t*>(smem + PP_F * PP_U_BYTES);
+    const int cam = blockIdx.z % C, group = blockIdx.z / C;
     const int x0 = blockIdx.x * PP_TX, y0 = blockIdx.y * PP_TY;
     PPFrame f;
-    f.raw = raw_frames + (size_t)img * in_w * in_h * 3;
+    f.n_frames = 0;
+#pragma unroll
+    for (int k = 0; k < PP_F; ++k) {
+        const long long img = (long long)(group * PP_F + k) * C + cam;
+        const bool in = img < n_images;
+        f.raw[k] = in ? raw_frames + (size_t)img * in_w * in_h * 3 : nullptr;
+        f.out[k] = (in && out) ? out + (size_t)img * S * S * 3 : nullptr;
+        f.gray[k] = (in && gray) ? gray + (size_t)img * S * S : nullptr;
+        f.n_frames += in ? 1 : 0;
+    }
     f.m1 = m1; f.m2 = m2; f.map_offset = cam * S * S;
-    f.out = out ? out + (size_t)img * S * S * 3 : nullptr;
-    f.gray = gray ? gray + (size_t)img * S * S : nullptr;
     f.in_w = in_w; f.in_h = in_h; f.S = S; f.rot = rotation[cam]; f.ay = (S - in_h) / 2;
     f.word_stores = word_stores;
     // the thread index is made opaque: knowing it is below 1024 the compiler narrows the item arithmetic of
@@ -50,13 +59,18 @@ k_preprocess(const uint8_t* __restrict__ raw_frames, int C, int in_w, int in_h, 
     const int nt = 256;
     pp_stage_undistort(f, U, x0, y0, tid, nt);
     __syncthreads();
-    for (int c0 = 0; c0 < 3; c0 += PP_GHT_CH) {
-        pp_stage_blur_h(U, GhT, c0, tid, nt);
-        __syncthreads();
-        pp_stage_blur_v(GhT, G, c0, tid, nt);
-        __syncthreads();
-    }
-    pp_stage_sharpen_store(f, G, x0, y0, tid, nt);
+#pragma unroll
+    for (int k = 0; k < PP_F; ++k) {
+        if (k >= f.n_frames) break;
+        uint8_t* Uk = U + k * PP_U_BYTES;                               // G over U (dead after the horizontal pass)
+        for (int c0 = 0; c0 < 3; c0 += PP_GHT_CH) {
+            pp_stage_blur_h(Uk, GhT, c0, tid, nt);
+            __syncthreads();
+            pp_stage_blur_v(GhT, Uk, c0, tid, nt);
+            __syncthreads();
+        }
+        pp_stage_sharpen_store(f, k, Uk, x0, y0, tid, nt);              // the next frame's horizontal pass may start
+    }                                                                   // meanwhile: it writes GhT, reads its own U
 }
 
 // cv.initUndistortRectifyMap(K, dist, I, K, (S, S), CV_16SC2): per output pixel the source position
@@ -128,14 +142,17 @@ int mocap_get_undistort_map(mocap_ctx* ctx, int cam, int16_t* m1, uint16_t* m2) 
 
 // processed frames and/or the grayscale plane S1 derives from them
 static int launch_preprocess(mocap_ctx* ctx, const uint8_t* raw_frames, int n_images, uint8_t* out_frames, uint8_t* gray) {
-    const int S = ctx->cfg.width;
-    for (int i0 = 0; i0 < n_images; i0 += 65535) {            // gridDim.z
-        const int n = n_images - i0 < 65535 ? n_images - i0 : 65535;
+    const int S = ctx->cfg.width, C = ctx->cfg.n_cam;
+    const int groups_per_launch = 65535 / C > 0 ? 65535 / C : 1;           // gridDim.z <= 65535
+    const int per_launch = groups_per_launch * PP_F * C;                    // whole frame-sets, whole groups
+    for (int i0 = 0; i0 < n_images; i0 += per_launch) {
+        const int n = n_images - i0 < per_launch ? n_images - i0 : per_launch;
+        const int sets = (n + C - 1) / C, groups = (sets + PP_F - 1) / PP_F;
         uint8_t* o = out_frames ? out_frames + (size_t)i0 * S * S * 3 : nullptr;
         uint8_t* g = gray ? gray + (size_t)i0 * S * S : nullptr;
         const int word_stores = (S % 4 == 0) && (reinterpret_cast<uintptr_t>(o) % 4 == 0) && (reinterpret_cast<uintptr_t>(g) % 4 == 0);
-        k_preprocess<<<dim3((S + PP_TX - 1) / PP_TX, (S + PP_TY - 1) / PP_TY, n), 256, 0, ctx->stream>>>(
-            raw_frames + (size_t)i0 * ctx->pp_in_w * ctx->pp_in_h * 3, ctx->cfg.n_cam, ctx->pp_in_w, ctx->pp_in_h, S, ctx->d_pp_rot,
+        k_preprocess<<<dim3((S + PP_TX - 1) / PP_TX, (S + PP_TY - 1) / PP_TY, groups * C), 256, 0, ctx->stream>>>(
+            raw_frames + (size_t)i0 * ctx->pp_in_w * ctx->pp_in_h * 3, n, C, ctx->pp_in_w, ctx->pp_in_h, S, ctx->d_pp_rot,
             reinterpret_cast<const int32_t*>(ctx->d_pp_m1), ctx->d_pp_m2, o, g, word_stores);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches += 1;

@@ -30,6 +30,9 @@
 #define PP_UNROLL
 #endif
 
+#ifndef PP_F
+#define PP_F 2                             // frames of ONE camera per CTA: a pixel's map decode is shared by them
+#endif
 #define PP_TX 64
 #ifndef PP_TY
 #define PP_TY 64                           // multiple of 4 (64x64: 48 KB of shared memory, 1.41x apron overhead; 64x32: 28 KB, 1.63x)
@@ -45,19 +48,20 @@
 #endif                                     // PP_GHT_CH channels; 1 keeps the tile at 28 KB so that 5 CTAs are resident
 #define PP_GHT_BYTES (PP_GHT_CH * PP_GW * PP_GHT_STRIDE * 4)
 #define PP_G_BYTES (3 * PP_GH * PP_GW)
-// G reuses U's bytes: U is dead once the horizontal pass has run, G is born in the vertical pass
-#define PP_SMEM_BYTES (PP_U_BYTES + PP_GHT_BYTES)
+// one U per frame; G reuses its frame's U: U is dead once the horizontal pass has run, G is born in the vertical pass
+#define PP_SMEM_BYTES (PP_F * PP_U_BYTES + PP_GHT_BYTES)
 static_assert(PP_G_BYTES <= PP_U_BYTES && PP_U_BYTES % 4 == 0 && PP_TY % 4 == 0 && PP_TX % 4 == 0, "tile layout");
 
 struct PPFrame {
-    const uint8_t* raw;        // [in_h][in_w][3] raw camera frame
+    const uint8_t* raw[PP_F];  // [in_h][in_w][3] raw frames of ONE camera (consecutive frame-sets)
+    uint8_t* out[PP_F];        // [S][S][3] processed frames, or null
+    uint8_t* gray[PP_F];       // [S][S] what _find_dot's cvtColor(RGB2GRAY) makes of the processed frame, or null
+    int n_frames;              // 1 .. PP_F entries of the arrays above are in use
     const int32_t* m1;         // [n_cam][S][S] (sy << 16) | (sx & 0xffff): integer source coordinates of cv2's fixed-point map
     const uint16_t* m2;        // [n_cam][S][S] (fy << 5) | fx, the 1/32 px fractions
-    uint8_t* out;              // [S][S][3] processed frame, or null
-    uint8_t* gray;             // [S][S] what _find_dot's cvtColor(RGB2GRAY) makes of the processed frame, or null
     int in_w, in_h, S, rot, ay;
     int map_offset;            // cam * S * S: where this camera's map starts in m1 / m2
-    int word_stores;           // out rows are 4-byte aligned (S % 4 == 0 and aligned base)
+    int word_stores;           // out / gray rows are 4-byte aligned (S % 4 == 0 and aligned bases)
 };
 
 // ---- packed dot products (native on the device, spelled out on the host) ---------------------------
@@ -168,42 +172,61 @@ PP_HD void pp_stage_undistort(const PPFrame& f, uint8_t* U, int x0, int y0, int 
         const int fx = fr & 31, fy = (fr >> 5) & 31;
         const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy), w10 = (32 - fx) * fy, w11 = fx * fy;
         const int ry = sy - f.ay;
-        int v0 = 512, v1 = 512, v2 = 512;
+        // everything above is per PIXEL OF THE CAMERA; the frames of this camera only differ in the bytes read
         if ((unsigned)sx < (unsigned)(S - 1) && (unsigned)ry < (unsigned)(f.in_h - 1)) {
             // all four taps inside the camera frame proper: two row pointers, constant byte offsets
-            if (f.rot == 2) {
-                const uint8_t* p = f.raw + ((f.in_h - 1 - ry) * f.in_w + (f.in_w - 1 - sx)) * 3;
-                const uint8_t* q = p - 3 * f.in_w;
-                v0 += p[0] * w00 + p[-3] * w01 + q[0] * w10 + q[-3] * w11;
-                v1 += p[1] * w00 + p[-2] * w01 + q[1] * w10 + q[-2] * w11;
-                v2 += p[2] * w00 + p[-1] * w01 + q[2] * w10 + q[-1] * w11;
-            } else {
-                const uint8_t* p = f.raw + (ry * f.in_w + sx) * 3;
-                const uint8_t* q = p + 3 * f.in_w;
-                v0 += p[0] * w00 + p[3] * w01 + q[0] * w10 + q[3] * w11;
-                v1 += p[1] * w00 + p[4] * w01 + q[1] * w10 + q[4] * w11;
-                v2 += p[2] * w00 + p[5] * w01 + q[2] * w10 + q[5] * w11;
+            const bool flip = f.rot == 2;
+            const int o = flip ? ((f.in_h - 1 - ry) * f.in_w + (f.in_w - 1 - sx)) * 3 : (ry * f.in_w + sx) * 3;
+            PP_UNROLL
+            for (int k = 0; k < PP_F; ++k) {
+                if (k >= f.n_frames) break;
+                const uint8_t* p = f.raw[k] + o;
+                int v0, v1, v2;
+                if (flip) {
+                    const uint8_t* q = p - 3 * f.in_w;
+                    v0 = p[0] * w00 + p[-3] * w01 + q[0] * w10 + q[-3] * w11;
+                    v1 = p[1] * w00 + p[-2] * w01 + q[1] * w10 + q[-2] * w11;
+                    v2 = p[2] * w00 + p[-1] * w01 + q[2] * w10 + q[-1] * w11;
+                } else {
+                    const uint8_t* q = p + 3 * f.in_w;
+                    v0 = p[0] * w00 + p[3] * w01 + q[0] * w10 + q[3] * w11;
+                    v1 = p[1] * w00 + p[4] * w01 + q[1] * w10 + q[4] * w11;
+                    v2 = p[2] * w00 + p[5] * w01 + q[2] * w10 + q[5] * w11;
+                }
+                uint8_t* u = U + k * PP_U_BYTES + i;       // i == ty * PP_UW + tx
+                u[0] = (uint8_t)((v0 + 512) >> 10);
+                u[PP_UH * PP_UW] = (uint8_t)((v1 + 512) >> 10);
+                u[2 * PP_UH * PP_UW] = (uint8_t)((v2 + 512) >> 10);
             }
-        } else if ((unsigned)(ry + 9) < (unsigned)(f.in_h + 17)) {
+        } else {
             // rows -9 .. in_h + 7: the feathered rows, the frame edge or the side border, tap by tap (rare, kept
             // compact); anything further out is the zero padding of make_square and stays 0
+            const bool some = (unsigned)(ry + 9) < (unsigned)(f.in_h + 17);
+            PP_UNROLL
+            for (int k = 0; k < PP_F; ++k) {                // unrolled so that f.raw[k] stays in registers
+                if (k >= f.n_frames) break;
+                int v0 = 512, v1 = 512, v2 = 512;
+                if (some) {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-            for (int t = 0; t < 4; ++t) {
-                int o;
-                const int s8 = pp_squared_tap(f, sy + (t >> 1), sx + (t & 1), o);
-                if (s8 == 0) continue;
-                const int w = t == 0 ? w00 : t == 1 ? w01 : t == 2 ? w10 : w11;
-                v0 += ((f.raw[o + 0] * s8) >> 3) * w;      // exact: the feather factor is a multiple of 1/8
-                v1 += ((f.raw[o + 1] * s8) >> 3) * w;
-                v2 += ((f.raw[o + 2] * s8) >> 3) * w;
+                    for (int t = 0; t < 4; ++t) {
+                        int o;
+                        const int s8 = pp_squared_tap(f, sy + (t >> 1), sx + (t & 1), o);
+                        if (s8 == 0) continue;
+                        const int w = t == 0 ? w00 : t == 1 ? w01 : t == 2 ? w10 : w11;
+                        const uint8_t* p = f.raw[k] + o;
+                        v0 += ((p[0] * s8) >> 3) * w;      // exact: the feather factor is a multiple of 1/8
+                        v1 += ((p[1] * s8) >> 3) * w;
+                        v2 += ((p[2] * s8) >> 3) * w;
+                    }
+                }
+                uint8_t* u = U + k * PP_U_BYTES + i;
+                u[0] = (uint8_t)(v0 >> 10);
+                u[PP_UH * PP_UW] = (uint8_t)(v1 >> 10);
+                u[2 * PP_UH * PP_UW] = (uint8_t)(v2 >> 10);
             }
         }
-        uint8_t* u = U + i;                                // == ty * PP_UW + tx
-        u[0] = (uint8_t)(v0 >> 10);
-        u[PP_UH * PP_UW] = (uint8_t)(v1 >> 10);
-        u[2 * PP_UH * PP_UW] = (uint8_t)(v2 >> 10);
     }
 }
 
@@ -254,7 +277,7 @@ PP_HD void pp_stage_blur_v(const uint32_t* GhT, uint8_t* G, int c0, int tid, int
 
 // ---- stage 3: cv.filter2D with the 5x5 kernel (integer correlation, saturate), cvtColor RGB2BGR, store.
 // One item = 4 neighbouring output pixels, all 3 channels = 12 contiguous output bytes.
-PP_HD void pp_stage_sharpen_store(const PPFrame& f, const uint8_t* G, int x0, int y0, int tid, int nt) {
+PP_HD void pp_stage_sharpen_store(const PPFrame& f, int k, const uint8_t* G, int x0, int y0, int tid, int nt) {
     const uint32_t* Gw = reinterpret_cast<const uint32_t*>(G);
     const int NG = PP_TX / 4;
     for (int i = tid; i < NG * PP_TY; i += nt) {
@@ -278,8 +301,8 @@ PP_HD void pp_stage_sharpen_store(const PPFrame& f, const uint8_t* G, int x0, in
             for (int j = 0; j < 4; ++j) a[c][j] = a[c][j] < 0 ? 0 : (a[c][j] > 255 ? 255 : a[c][j]);
         }
         // RGB -> BGR (helpers.py:82): byte order per pixel is channel 2, 1, 0
-        if (f.out) {
-            uint8_t* o = f.out + ((size_t)y * f.S + x) * 3;
+        if (f.out[k]) {
+            uint8_t* o = f.out[k] + ((size_t)y * f.S + x) * 3;
             if (f.word_stores) {
                 uint32_t* ow = reinterpret_cast<uint32_t*>(o);
                 ow[0] = (uint32_t)a[2][0] | ((uint32_t)a[1][0] << 8) | ((uint32_t)a[0][0] << 16) | ((uint32_t)a[2][1] << 24);
@@ -293,11 +316,11 @@ PP_HD void pp_stage_sharpen_store(const PPFrame& f, const uint8_t* G, int x0, in
         }
         // S1 reads the processed frame through cv2's RGB2GRAY (helpers.py:144), 15-bit fixed point with byte 0
         // as "R": emitting that plane here lets the marker pipeline read 1 byte per pixel instead of 3
-        if (f.gray) {
+        if (f.gray[k]) {
             uint32_t gq[4];
             PP_UNROLL
             for (int j = 0; j < 4; ++j) gq[j] = (uint32_t)(a[2][j] * 9798 + a[1][j] * 19235 + a[0][j] * 3735 + 16384) >> 15;
-            uint8_t* o = f.gray + (size_t)y * f.S + x;
+            uint8_t* o = f.gray[k] + (size_t)y * f.S + x;
             if (f.word_stores) *reinterpret_cast<uint32_t*>(o) = gq[0] | (gq[1] << 8) | (gq[2] << 16) | (gq[3] << 24);
             else for (int j = 0; j < 4 && x + j < f.S; ++j) o[j] = (uint8_t)gq[j];
         }

@@ -231,16 +231,22 @@ def test_preprocess_tile_stages_equal_cv2_chain_on_host(preproc_host, S, in_h, r
     m1 = np.ascontiguousarray(m1); m2 = np.ascontiguousarray(m2)
     port = RefPort([K])
     rng = np.random.default_rng(S + rot)
-    frames = [rng.integers(0, 256, size=(in_h, S, 3), dtype=np.uint8), np.full((in_h, S, 3), 255, dtype=np.uint8),
-              (rng.integers(0, 2, size=(in_h, S, 3)) * 255).astype(np.uint8)]
-    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    for raw in frames:
-        want = port.preprocess(raw, 0, dist, rot)
-        got = np.full((S, S, 3), 7, dtype=np.uint8)
-        gray = np.full((S, S), 7, dtype=np.uint8)
-        preproc_host.hc_preprocess(p(raw), S, in_h, S, rot, p(m1), p(m2), p(got), p(gray), word_stores if S % 4 == 0 else 0, n_threads)
-        assert np.array_equal(got, want), (np.argwhere(got != want)[:5], int((got != want).sum()))
-        assert np.array_equal(gray, cv2.cvtColor(want, cv2.COLOR_RGB2GRAY))      # what _find_dot thresholds (helpers.py:144)
-        only_gray = np.zeros((S, S), dtype=np.uint8)
-        preproc_host.hc_preprocess(p(raw), S, in_h, S, rot, p(m1), p(m2), None, p(only_gray), word_stores if S % 4 == 0 else 0, n_threads)
-        assert np.array_equal(only_gray, gray)
+    frames = np.stack([rng.integers(0, 256, size=(in_h, S, 3), dtype=np.uint8), np.full((in_h, S, 3), 255, dtype=np.uint8),
+                       (rng.integers(0, 2, size=(in_h, S, 3)) * 255).astype(np.uint8)])
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+    ws = word_stores if S % 4 == 0 else 0
+    want = np.stack([port.preprocess(raw, 0, dist, rot) for raw in frames])
+    want_gray = np.stack([cv2.cvtColor(w, cv2.COLOR_RGB2GRAY) for w in want])        # what _find_dot thresholds (helpers.py:144)
+    # the kernel handles the frames of one camera in groups: 3 frames = a full group and a ragged one (for a
+    # group size of 2); then each frame on its own
+    for n in (3, 1):
+        for first in range(0, 3, n):
+            raw = np.ascontiguousarray(frames[first:first + n])
+            got = np.full((n, S, S, 3), 7, dtype=np.uint8)
+            gray = np.full((n, S, S), 7, dtype=np.uint8)
+            preproc_host.hc_preprocess(p(raw), n, S, in_h, S, rot, p(m1), p(m2), p(got), p(gray), ws, n_threads)
+            assert np.array_equal(got, want[first:first + n]), int((got != want[first:first + n]).sum())
+            assert np.array_equal(gray, want_gray[first:first + n])
+            only_gray = np.zeros((n, S, S), dtype=np.uint8)
+            preproc_host.hc_preprocess(p(raw), n, S, in_h, S, rot, p(m1), p(m2), None, p(only_gray), ws, n_threads)
+            assert np.array_equal(only_gray, gray)
