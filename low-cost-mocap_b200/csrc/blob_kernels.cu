@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(NT)
 k_blob_reduce(uint32_t* __restrict__ seg_count, const uint32_t* __restrict__ seg_list, int E, int W, int H,
               int max_blobs, int32_t* __restrict__ blob_xy, int32_t* __restrict__ blob_n,
               int64_t* __restrict__ blob_mom, int32_t* __restrict__ img_flags,
-              const uint32_t* __restrict__ worklist, uint32_t* __restrict__ work_count, uint32_t* __restrict__ done_count) {
+              const uint32_t* __restrict__ worklist, uint32_t* __restrict__ work_count, uint32_t* __restrict__ done_count,
+              int stat_images, unsigned long long* __restrict__ stat_acc, unsigned long long* __restrict__ stat_host) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BlobSmem sm = carve_blob_smem(smem_raw, E);
     const unsigned n_work = *work_count;
@@ -176,9 +177,25 @@ k_blob_reduce(uint32_t* __restrict__ seg_count, const uint32_t* __restrict__ seg
                                blob_mom ? blob_mom + (size_t)img * max_blobs * 4 : nullptr, ofl, flags);
         __syncthreads();
     }
+    // statistic for the host's choice of pipeline for the NEXT batch: blobs found in this batch (images this very
+    // launch is still reducing may be missed: it only steers a heuristic), left in mapped host memory by the last CTA
+    if (stat_host) {
+        unsigned long long local = 0;
+        for (int i = blockIdx.x * NT + threadIdx.x; i < stat_images; i += gridDim.x * NT) local += (unsigned)__ldcg(blob_n + i);
+        for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(stat_acc, local);
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {                                     // the last CTA to finish re-arms the worklist
         __threadfence();
-        if (atomicAdd(done_count, 1u) == gridDim.x - 1) { *work_count = 0; *done_count = 0; }
+        if (atomicAdd(done_count, 1u) == gridDim.x - 1) {
+            *work_count = 0; *done_count = 0;
+            if (stat_host) {
+                __threadfence();
+                stat_host[0] = atomicExch(stat_acc, 0ull);
+                stat_host[1] = (unsigned long long)stat_images;
+            }
+        }
     }
 }
 
@@ -238,7 +255,7 @@ int launch_detect(mocap_ctx* ctx, const uint8_t* frames, int n_images, int chann
             ctx->d_worklist, ctx->d_work_count);
     CUDA_TRY(ctx, cudaGetLastError());
     {
-        const int st = launch_blob_fallback(ctx, blob_xy, blob_n, blob_mom, img_flags);
+        const int st = launch_blob_fallback(ctx, blob_xy, blob_n, blob_mom, img_flags, n_images);
         if (st) return st;
     }
     ctx->launches += 2;      // stream kernel + warp-level reduce (the fallback counted itself)
@@ -246,7 +263,7 @@ int launch_detect(mocap_ctx* ctx, const uint8_t* frames, int n_images, int chann
 }
 
 // full-size reduction of the images on the worklist (exits at once when the list is empty)
-int launch_blob_fallback(mocap_ctx* ctx, int32_t* blob_xy, int32_t* blob_n, int64_t* blob_mom, int32_t* img_flags) {
+int launch_blob_fallback(mocap_ctx* ctx, int32_t* blob_xy, int32_t* blob_n, int64_t* blob_mom, int32_t* img_flags, int n_images) {
     const mocap_config& c = ctx->cfg;
     constexpr int NT = 128;
     const int E = c.max_segments;
@@ -257,11 +274,13 @@ int launch_blob_fallback(mocap_ctx* ctx, int32_t* blob_xy, int32_t* blob_n, int6
     if (wide)
         k_blob_reduce<NT, true><<<grid2, NT, smem, ctx->stream>>>(ctx->d_seg_count, ctx->d_seg_list, E, c.width, c.height,
                                                                c.max_blobs, blob_xy, blob_n, blob_mom, img_flags,
-                                                               ctx->d_worklist, ctx->d_work_count, ctx->d_work_count + 1);
+                                                               ctx->d_worklist, ctx->d_work_count, ctx->d_work_count + 1,
+                                                               n_images, ctx->d_stat_acc, ctx->pipeline_auto ? ctx->d_stat_host : nullptr);
     else
         k_blob_reduce<NT, false><<<grid2, NT, smem, ctx->stream>>>(ctx->d_seg_count, ctx->d_seg_list, E, c.width, c.height,
                                                                 c.max_blobs, blob_xy, blob_n, blob_mom, img_flags,
-                                                                ctx->d_worklist, ctx->d_work_count, ctx->d_work_count + 1);
+                                                                ctx->d_worklist, ctx->d_work_count, ctx->d_work_count + 1,
+                                                               n_images, ctx->d_stat_acc, ctx->pipeline_auto ? ctx->d_stat_host : nullptr);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 1;
     return MOCAP_OK;

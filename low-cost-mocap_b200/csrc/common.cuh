@@ -48,6 +48,10 @@ struct mocap_ctx {
     int       fused_ctas_per_sm;
     int       tma_ctas_per_sm;   // 0: bulk-copy kernel unavailable for this configuration
     int       use_tma;           // MOCAP_PIPELINE=tma: stream through the bulk-copy ring kernel
+    int       pipeline_auto;     // MOCAP_PIPELINE unset: heavy batches (many blobs per frame-set) take the three-kernel pipeline
+    unsigned long long* d_stat_acc;                  // device accumulator of the blob statistic
+    volatile unsigned long long* h_stat;             // pinned, mapped: {blobs, images} of the last batch, written by the GPU
+    unsigned long long* d_stat_host;                 // device alias of h_stat
     int       use_fused;      // 1: single fused pipeline kernel for 1-channel frames (default)
     int32_t*  d_blob_xy;
     int32_t*  d_blob_n;
@@ -91,7 +95,10 @@ int launch_triangulate(mocap_ctx* ctx, const double* obs, const uint8_t* mask, i
 int ensure_scratch(mocap_ctx* ctx, size_t bytes);
 int launch_locate(mocap_ctx* ctx, const double* obj, const double* err, const int32_t* n_obj, int n_sets,
                   int max_objects, double* out, int32_t* drone_index, int32_t* n_out);
-int launch_blob_fallback(mocap_ctx* ctx, int32_t* blob_xy, int32_t* blob_n, int64_t* blob_mom, int32_t* img_flags);
+int launch_blob_fallback(mocap_ctx* ctx, int32_t* blob_xy, int32_t* blob_n, int64_t* blob_mom, int32_t* img_flags, int n_images);
+// frame-sets with more blobs than this (average of the previous batch) are cheaper through the three-kernel
+// pipeline: the matcher's large code then runs in a kernel of its own instead of evicting the stream loop
+#define MOCAP_HEAVY_BLOBS_PER_SET 48
 int launch_match_list(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n, const uint32_t* set_list, uint32_t* set_count,
                       int n_sets_max, double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
 int launch_pipeline_tma(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int threshold,

@@ -147,7 +147,7 @@ int launch_pipeline_fused(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int
     ctx->launches += 1;
     // slow path for whatever exceeded the warp-level capacities (normally nothing: both kernels
     // read an empty worklist and exit)
-    int st = launch_blob_fallback(ctx, ctx->d_blob_xy, ctx->d_blob_n, nullptr, ctx->d_img_flags);
+    int st = launch_blob_fallback(ctx, ctx->d_blob_xy, ctx->d_blob_n, nullptr, ctx->d_img_flags, n_sets * ctx->cfg.n_cam);
     if (st) return st;
     st = launch_match_list(ctx, ctx->d_blob_xy, ctx->d_blob_n, ctx->d_set_worklist, ctx->d_work_count + 2, n_sets,
                            obj, err, n_obj, set_flags);

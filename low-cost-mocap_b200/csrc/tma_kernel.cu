@@ -238,7 +238,7 @@ int launch_pipeline_tma(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int t
         ctx->tim_used += 1;
     }
     ctx->launches += 1;
-    int st = launch_blob_fallback(ctx, ctx->d_blob_xy, ctx->d_blob_n, nullptr, ctx->d_img_flags);
+    int st = launch_blob_fallback(ctx, ctx->d_blob_xy, ctx->d_blob_n, nullptr, ctx->d_img_flags, n_sets * ctx->cfg.n_cam);
     if (st) return st;
     return launch_match_list(ctx, ctx->d_blob_xy, ctx->d_blob_n, ctx->d_set_worklist, ctx->d_work_count + 2, n_sets,
                              obj, err, n_obj, set_flags);

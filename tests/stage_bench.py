@@ -55,7 +55,7 @@ def config3_pipeline():
     return {"workload": "8 cameras, 16 markers, 4000 frame-sets of 640x480 (9.8 GB resident)", "ms_per_batch": ms,
             "frame_sets_per_s": B / ms * 1e3, "hbm_gbs": B * C * 307200 / ms / 1e6, "points_per_frame_set": float(n.mean()),
             "overflow_flags": int((flags != 0).sum()), "cpu_reference_ms_per_frame_set_1core": cpu_ms,
-            "pipeline": os.environ.get("MOCAP_PIPELINE", "fused")}
+            "pipeline": os.environ.get("MOCAP_PIPELINE", "auto (single-pass kernel first, three-kernel pipeline after a heavy batch)")}
 
 
 def colour_pipeline():

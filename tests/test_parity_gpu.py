@@ -985,3 +985,31 @@ def test_error_behaviour(torch):
     ctx.set_cameras([np.eye(3)] * 2, [{"R": np.eye(3), "t": np.zeros(3)}] * 2)
     out = ctx.pipeline(frames)                                 # empty frames: zero points, no error
     assert int(out["n"][0]) == 0 and int(out["flags"][0]) == 0
+
+
+def test_heavy_batches_take_the_three_kernel_pipeline(torch, monkeypatch):
+    """With MOCAP_PIPELINE unset the context picks the pipeline per batch from the blob count of the previous
+    batch (mapped host memory, no synchronisation): light frame-sets stay on the single-pass kernel (3 launches
+    per batch), heavy ones (8 cameras x 16 markers) move to the three-kernel pipeline (4 launches) from the
+    second batch on -- with identical results."""
+    monkeypatch.delenv("MOCAP_PIPELINE", raising=False)
+    for C, M, heavy in ((8, 16, True), (4, 4, False)):
+        frames, truth, poses, K = synth.make_frame_pool(C, M, 6, seed=3)
+        ctx = pkg.MocapContext(C, 640, 480, max_roots=64)
+        ctx.set_cameras([K] * C, poses)
+        batch = torch.from_numpy(frames).cuda()
+        outs, launches = [], []
+        for _ in range(3):
+            before = ctx.launch_count()
+            o = ctx.pipeline(batch)
+            torch.cuda.synchronize()
+            launches.append(ctx.launch_count() - before)
+            outs.append({k: v.cpu().numpy() for k, v in o.items()})
+        assert launches[0] == 3 and launches[1] == launches[2] == (4 if heavy else 3), launches
+        n = outs[0]["n"]
+        assert n.sum() > 0
+        for o in outs[1:]:
+            assert np.array_equal(o["n"], n) and np.array_equal(o["flags"], outs[0]["flags"])
+            for b in range(len(n)):
+                assert np.array_equal(o["obj"][b, :n[b]], outs[0]["obj"][b, :n[b]])
+                assert np.array_equal(o["err"][b, :n[b]], outs[0]["err"][b, :n[b]])
