@@ -167,11 +167,13 @@ def run_reference_arm(args):
     _W["frames"] = frames
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_cpu_init, initargs=(K, poses)) as pool_obj:
-        # size one step to ~4 s of wall time on this box
+        # size one step so that the whole run (K timed steps + W quarter-size warm-up steps) takes about two
+        # and a half minutes on this box, and no step more than ~4 s
         cpu_pass(pool_obj, frames, cores * 2)                      # spin the workers up
         t_probe, _ = cpu_pass(pool_obj, frames, cores * 2)
         per_set = t_probe / (cores * 2)
-        sample = int(min(BATCH, max(cores * 4, 4.0 / per_set)))
+        step_s = min(4.0, max(0.25, 150.0 / (args.steps + 0.25 * args.warmup)))
+        sample = int(min(BATCH, max(cores * 4, step_s / per_set)))
         for _ in range(args.warmup):
             cpu_pass(pool_obj, frames, max(cores, sample // 4))
         t = 0.0
