@@ -250,3 +250,31 @@ def test_preprocess_tile_stages_equal_cv2_chain_on_host(preproc_host, S, in_h, r
             only_gray = np.zeros((n, S, S), dtype=np.uint8)
             preproc_host.hc_preprocess(p(raw), n, S, in_h, S, rot, p(m1), p(m2), None, p(only_gray), ws, n_threads)
             assert np.array_equal(only_gray, gray)
+
+
+def test_preprocess_tile_stages_fuzz_on_host(preproc_host):
+    """Random small geometries through the host-stepped tile stages against the cv2 chain: sizes that are not a
+    multiple of 4 or of the tile, the tallest frame make_square accepts (8 pad rows), strong distortion (map
+    coordinates far outside the frame), both rotations, several thread counts."""
+    import cv2
+    from oracle.ref_port import RefPort
+    rng = np.random.default_rng(2024)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+    for case in range(24):
+        S = int(rng.integers(34, 150))
+        in_h = int(rng.integers(1, S - 15)) if case % 4 else S - 16
+        rot = int(rng.choice([0, 2]))
+        f0 = float(rng.uniform(0.5, 1.5) * S)
+        K = np.array([[f0, 0, S / 2.0 + rng.uniform(-5, 5)], [0, f0 * rng.uniform(0.9, 1.1), S / 2.0 + rng.uniform(-5, 5)], [0, 0, 1]])
+        dist = np.array([-0.126, 0.263, 0.0012, 0.0002, -0.249]) * rng.uniform(-3.0, 3.0)
+        m1, m2 = cv2.initUndistortRectifyMap(K, dist, np.eye(3), K, (S, S), cv2.CV_16SC2)
+        m1 = np.ascontiguousarray(m1); m2 = np.ascontiguousarray(m2)
+        raw = rng.integers(0, 256, size=(2, in_h, S, 3), dtype=np.uint8)
+        port = RefPort([K])
+        want = np.stack([port.preprocess(r, 0, dist, rot) for r in raw])
+        got = np.full((2, S, S, 3), 9, dtype=np.uint8)
+        gray = np.full((2, S, S), 9, dtype=np.uint8)
+        preproc_host.hc_preprocess(p(raw), 2, S, in_h, S, rot, p(m1), p(m2), p(got), p(gray), 1 if S % 4 == 0 else 0,
+                                   int(rng.choice([32, 96, 256])))
+        assert np.array_equal(got, want), (case, S, in_h, rot, int((got != want).sum()))
+        assert np.array_equal(gray, np.stack([cv2.cvtColor(w, cv2.COLOR_RGB2GRAY) for w in want])), (case, S, in_h, rot)
