@@ -1,0 +1,117 @@
+// Test-only SIMT emulation: lets the warp- and CTA-synchronous DEVICE code of the product headers
+// (csrc/blob_device.cuh, csrc/match_device.cuh) run unchanged on the host, one std::thread per CUDA thread,
+// so that the algorithms the kernels execute can be checked against the oracle on a machine without a GPU.
+// Barriers and warp collectives are rendezvous points of the participating threads; shared-memory atomics
+// are host atomics on plain memory.  Only what those headers use is provided.  NOT part of libmocap_b200.so.
+#pragma once
+#include <cuda_runtime.h>          // vector types, attribute macros (the CUDA intrinsics are not declared for g++)
+#include <stdint.h>
+#include <string.h>
+#include <atomic>
+#include <barrier>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+namespace simt {
+
+struct Block {
+    int nt;
+    std::barrier<> cta;
+    std::vector<std::unique_ptr<std::barrier<>>> warp;
+    std::vector<unsigned long long> xchg;            // one slot per thread for the warp collectives
+    explicit Block(int n) : nt(n), cta(n), xchg(n) {
+        for (int w = 0; w < (n + 31) / 32; ++w) {
+            const int members = (w + 1) * 32 <= n ? 32 : n - w * 32;
+            warp.emplace_back(new std::barrier<>(members));
+        }
+    }
+};
+struct Tid { unsigned x, y, z; };
+inline thread_local Tid tid{0, 0, 0};
+inline thread_local Block* blk = nullptr;
+
+inline void warp_sync() { blk->warp[tid.x >> 5]->arrive_and_wait(); }
+inline unsigned long long exchange(unsigned long long v, int src_lane) {      // value of lane src_lane of my warp
+    blk->xchg[tid.x] = v;
+    warp_sync();
+    const unsigned long long r = blk->xchg[(tid.x & ~31u) + (unsigned)src_lane];
+    warp_sync();
+    return r;
+}
+
+// run fn on nt threads that form one CTA (threadIdx.x = 0 .. nt-1)
+inline void launch(int nt, const std::function<void()>& fn) {
+    Block b(nt);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([&, t] { tid = Tid{(unsigned)t, 0, 0}; blk = &b; fn(); });
+    for (auto& t : th) t.join();
+}
+
+}  // namespace simt
+
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
+
+// ---- what the device headers call ------------------------------------------------------------------------
+#define threadIdx (simt::tid)
+inline void __syncthreads() { simt::blk->cta.arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_sync(); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+
+template <typename T> inline T __shfl_sync(unsigned, T v, int src) {
+    static_assert(sizeof(T) <= 8, "shuffle width");
+    unsigned long long raw = 0; memcpy(&raw, &v, sizeof(T));
+    raw = simt::exchange(raw, src & 31);
+    T r; memcpy(&r, &raw, sizeof(T)); return r;
+}
+template <typename T> inline T __shfl_up_sync(unsigned m, T v, unsigned d) {
+    const int lane = (int)(simt::tid.x & 31);
+    const T r = __shfl_sync(m, v, lane >= (int)d ? lane - (int)d : lane);
+    return r;
+}
+template <typename T> inline T __shfl_down_sync(unsigned m, T v, unsigned d) {
+    const int lane = (int)(simt::tid.x & 31);
+    return __shfl_sync(m, v, lane + (int)d < 32 ? lane + (int)d : lane);
+}
+template <typename T> inline T __shfl_xor_sync(unsigned m, T v, int x) { return __shfl_sync(m, v, (int)(simt::tid.x & 31) ^ x); }
+inline unsigned __ballot_sync(unsigned, int pred) {
+    simt::blk->xchg[simt::tid.x] = pred ? 1ull : 0ull;
+    simt::warp_sync();
+    unsigned r = 0;
+    const unsigned base = simt::tid.x & ~31u;
+    for (unsigned l = 0; l < 32 && base + l < (unsigned)simt::blk->nt; ++l) r |= (unsigned)simt::blk->xchg[base + l] << l;
+    simt::warp_sync();
+    return r;
+}
+inline unsigned __match_any_sync(unsigned, unsigned v) {
+    simt::blk->xchg[simt::tid.x] = v;
+    simt::warp_sync();
+    unsigned r = 0;
+    const unsigned base = simt::tid.x & ~31u;
+    for (unsigned l = 0; l < 32 && base + l < (unsigned)simt::blk->nt; ++l) r |= (simt::blk->xchg[base + l] == v ? 1u : 0u) << l;
+    simt::warp_sync();
+    return r;
+}
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+template <typename T> inline T __ldcg(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
+template <typename T> inline T __ldg(const T* p) { return *p; }
+
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicMin(unsigned* p, unsigned v) {
+    unsigned old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }

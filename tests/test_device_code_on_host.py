@@ -1,0 +1,130 @@
+"""The DEVICE code of the hot path, run unchanged on the host: tests/hostcheck/simt_emu.h gives every CUDA
+thread a std::thread (barriers and warp collectives are rendezvous points), so the warp-synchronous S1 code
+of csrc/blob_device.cuh -- packed threshold, radix / rank / bitonic sort, lock-free union-find, 2x2-cell
+moments, ranking -- is checked against the reference's golden vectors and cv2 on a machine without a GPU.
+(The GPU parity tests in test_parity_gpu.py run the same code on the device through the C ABI.)"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.util import ROOT, load_golden
+
+PIPE_CASES = ["pipe_c2_m1", "pipe_c4_m4", "pipe_c8_m16"]
+
+HC = os.path.join(ROOT, "tests", "hostcheck")
+CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+
+
+@pytest.fixture(scope="module")
+def blob_emu():
+    src = os.path.join(HC, "blob_emu_host.cpp")
+    out = os.path.join(HC, "libblob_emu.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O2", "-shared", "-fPIC", "-pthread", "-I" + CUDA_INC, "-Wno-attributes",
+                           "-fno-strict-aliasing", "-o", out, src])
+    lib = ctypes.CDLL(out)
+
+    def detect(img, threshold=51, max_blobs=64, E=1024, force_cta=0, seed=1):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        H, W = img.shape
+        xy = np.zeros((max_blobs, 2), np.int32); n = np.zeros(1, np.int32)
+        mom = np.zeros((max_blobs, 4), np.int64); fl = np.zeros(1, np.int32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        rc = lib.hc_blob_detect(p(img), W, H, int(threshold), max_blobs, E, force_cta, seed, p(xy), p(n), p(mom), p(fl))
+        assert rc >= 0, rc
+        return {"path": rc, "n": int(n[0]), "xy": xy[:n[0]].copy(), "mom": mom[:n[0]].copy(), "flags": int(fl[0])}
+    return detect
+
+
+@pytest.mark.parametrize("name", PIPE_CASES + ["blobs_irregular"])
+def test_blob_device_code_vs_reference_golden(blob_emu, name):
+    """Exact blob count, centres and order (helpers.py:143-163) on the reference's golden frames, through the
+    one-warp-per-image variant and through the 128-thread variant of the same device function."""
+    z = load_golden(name)
+    frames = z["frames"]
+    B, C = frames.shape[:2]
+    step = max(1, (B * C) // 24)                         # a spread of ~24 images per case keeps the CPU suite short
+    for idx in range(0, B * C, step):
+        b, c = divmod(idx, C)
+        k = int(z["blob_n"][b, c])
+        for force_cta in (0, 1):
+            d = blob_emu(frames[b, c], force_cta=force_cta, seed=idx)
+            assert d["flags"] == 0 and d["n"] == k, (b, c, force_cta)
+            assert np.array_equal(d["xy"], z["blob_xy"][b, c, :k]), (b, c, force_cta)
+
+
+def test_blob_device_code_moments_and_pixel_counts_vs_cv2(blob_emu):
+    """A2 / SX6 / SY6 are the integers cv.moments accumulates for the contour; the pixel count equals
+    cv2.connectedComponentsWithStats (8-connectivity)."""
+    import cv2
+    z = load_golden("blobs_irregular")
+    for f, frame in enumerate(z["frames"][:, 0]):
+        binary = (frame > 51).astype(np.uint8)
+        contours, _ = cv2.findContours(binary * 255, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+        _, lab, stats, _ = cv2.connectedComponentsWithStats(binary, connectivity=8)
+        kept = []
+        for cnt in contours:
+            m = cv2.moments(cnt)
+            if m["m00"] != 0:
+                x0, y0 = cnt[0, 0]
+                kept.append((round(m["m00"] * 2), round(m["m10"] * 6), round(m["m01"] * 6), stats[lab[y0, x0], cv2.CC_STAT_AREA]))
+        d = blob_emu(frame, seed=f)
+        assert d["n"] == len(kept)
+        for i, ref in enumerate(kept):
+            assert tuple(int(v) for v in d["mom"][i]) == ref, (f, i)
+
+
+@pytest.mark.parametrize("threshold", [0, 1, 50, 51, 52, 127, 128, 129, 200, 254, 255])
+def test_packed_threshold_is_strictly_greater(blob_emu, threshold):
+    """pix > threshold for every byte value: the packed compare has two regimes around 128, and the cheap
+    "any byte above?" test of the stream loop must agree with the per-pixel mask (checked inside the harness)."""
+    img = np.zeros((480, 640), np.uint8)
+    for v in range(256):                       # 256 isolated 2x2 squares, one per grey value
+        y, x = 8 + 12 * (v // 32), 8 + 12 * (v % 32)
+        img[y:y + 2, x:x + 2] = v
+    d = blob_emu(img, threshold=threshold, E=1024)
+    expect = 255 - threshold
+    assert d["n"] == min(expect, 64) and ((d["flags"] & 2) != 0) == (expect > 64)
+
+
+def test_capacity_paths_of_the_blob_code(blob_emu):
+    """More segments than a warp's slab, more blobs than a warp accumulates, a blob wider than a row index span,
+    a frame full of set pixels: the warp variant must decline (uniformly) and the CTA variant must finish; both
+    agree with the oracle's _find_dot."""
+    from oracle.ref_port import RefPort
+    port = RefPort([np.eye(3)])
+    rng = np.random.default_rng(3)
+    cases = []
+    a = np.zeros((480, 640), np.uint8)                     # 70 small blobs: > 64 warp accumulators
+    for k in range(70):
+        y, x = 10 + 6 * (k // 35), 20 + 16 * (k % 35)
+        a[y:y + 3, x:x + 3] = 255
+    cases.append(a)
+    b = np.zeros((480, 640), np.uint8); b[300:304, 100:400] = 255          # long thin blob
+    cases.append(b)
+    c = np.zeros((480, 640), np.uint8); c[40:440, 300:330] = 200           # tall blob: 400 rows, 800+ segments
+    cases.append(c)
+    d = np.zeros((480, 640), np.uint8)                     # irregular blobs grown by random walks
+    for _ in range(12):
+        y, x = int(rng.integers(40, 440)), int(rng.integers(40, 600))
+        for _ in range(150):
+            d[y - 1:y + 2, x - 1:x + 2] = 255
+            y = int(np.clip(y + rng.integers(-2, 3), 2, 477)); x = int(np.clip(x + rng.integers(-2, 3), 2, 637))
+    import cv2
+    d = cv2.morphologyEx(d, cv2.MORPH_CLOSE, np.ones((5, 5), np.uint8))   # solid blobs (no holes): the S1 contract
+    filled = d.copy()
+    contours, _ = cv2.findContours(d, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
+    cv2.drawContours(filled, contours, -1, 255, thickness=cv2.FILLED)
+    cases.append(filled)
+    for i, img in enumerate(cases):
+        ref = [q for q in port.find_dot(np.repeat(img[:, :, None], 3, axis=2)) if q[0] is not None]
+        got = blob_emu(img, max_blobs=64, E=4096, seed=i)
+        assert got["xy"].tolist() == ref[:64], i
+        assert got["n"] == min(len(ref), 64)
+        forced = blob_emu(img, max_blobs=64, E=4096, force_cta=1, seed=i)
+        assert forced["xy"].tolist() == got["xy"].tolist() and forced["n"] == got["n"]
+    assert blob_emu(cases[0], E=4096)["path"] == 2          # the warp variant declined 70 blobs
+    assert blob_emu(cases[2], E=4096)["path"] == 2          # and 800 segments
+    assert blob_emu(cases[1], E=4096)["path"] == 1
