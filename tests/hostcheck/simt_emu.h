@@ -96,6 +96,10 @@ inline unsigned __match_any_sync(unsigned, unsigned v) {
     simt::warp_sync();
     return r;
 }
+inline long long __double_as_longlong(double d) { long long r; memcpy(&r, &d, 8); return r; }
+inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
+inline int __float_as_int(float f) { int r; memcpy(&r, &f, 4); return r; }
+inline float __int_as_float(int v) { float r; memcpy(&r, &v, 4); return r; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }

@@ -128,3 +128,77 @@ def test_capacity_paths_of_the_blob_code(blob_emu):
     assert blob_emu(cases[0], E=4096)["path"] == 2          # the warp variant declined 70 blobs
     assert blob_emu(cases[2], E=4096)["path"] == 2          # and 800 segments
     assert blob_emu(cases[1], E=4096)["path"] == 1
+
+
+# ------------------------------------------------------------------------------------------------ S2 + S3
+X_TOL = 1e-7          # pose units (BASELINE north_star)
+ERR_RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def match_emu():
+    src = os.path.join(HC, "match_emu_host.cpp")
+    out = os.path.join(HC, "libmatch_emu.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O2", "-shared", "-fPIC", "-pthread", "-I" + CUDA_INC, "-Wno-attributes",
+                           "-fno-strict-aliasing", "-o", out, src])
+    lib = ctypes.CDLL(out)
+
+    def match(K, R, t, blob_xy, blob_n, max_roots=128, max_cands=8, max_groups=4096):
+        C = len(R)
+        B = blob_n.shape[0]
+        MB = blob_xy.shape[2]
+        K = np.ascontiguousarray(np.stack([K] * C) if np.ndim(K) == 2 else K, dtype=np.float64)
+        R = np.ascontiguousarray(R, dtype=np.float64); t = np.ascontiguousarray(np.reshape(t, (C, 3)), dtype=np.float64)
+        xy = np.ascontiguousarray(blob_xy, dtype=np.int32); n = np.ascontiguousarray(blob_n, dtype=np.int32)
+        obj = np.zeros((B, max_roots, 3)); err = np.zeros((B, max_roots))
+        k = np.zeros(B, np.int32); fl = np.zeros(B, np.int32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        assert lib.hc_match_triangulate(p(K), p(R), p(t), C, p(xy), p(n), B, MB, max_roots, max_cands, ctypes.c_uint(max_groups),
+                                        p(obj), p(err), p(k), p(fl)) == 0
+        return {"obj": obj, "err": err, "n": k, "flags": fl}
+    return match
+
+
+@pytest.mark.parametrize("name", PIPE_CASES)
+def test_matcher_device_code_vs_reference_golden(match_emu, name):
+    """find_point_correspondance_and_object_points (helpers.py:339-421) as the device code computes it, one
+    emulated warp per frame-set: same kept roots, 3D points within 1e-7 pose units, reprojection errors equal."""
+    z = load_golden(name)
+    d = match_emu(z["K"], z["R"], z["t"], z["blob_xy"], z["blob_n"])
+    k = d["n"]
+    assert np.array_equal(k, z["nroot"]) and not d["flags"].any()
+    for b in range(len(k)):
+        if k[b]:
+            assert np.abs(d["obj"][b, :k[b]] - z["obj"][b, :k[b]]).max() <= X_TOL
+            assert np.allclose(d["err"][b, :k[b]], z["err"][b, :k[b]], rtol=ERR_RTOL, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["pipe_c2_m1", "pipe_c4_m4"])
+def test_pixels_to_points_through_the_device_code_on_host(blob_emu, match_emu, name):
+    """The whole S1 -> S2 -> S3 chain of the kernels, from the golden FRAMES to 3D points, without a GPU."""
+    z = load_golden(name)
+    frames = z["frames"][:10]
+    B, C = frames.shape[:2]
+    xy = np.zeros((B, C, 64, 2), np.int32); n = np.zeros((B, C), np.int32)
+    for b in range(B):
+        for c in range(C):
+            d = blob_emu(frames[b, c], seed=b * C + c)
+            n[b, c] = d["n"]; xy[b, c, :d["n"]] = d["xy"]
+    assert np.array_equal(n, z["blob_n"][:B])
+    m = match_emu(z["K"], z["R"], z["t"], xy, n)
+    assert np.array_equal(m["n"], z["nroot"][:B])
+    for b in range(B):
+        k = m["n"][b]
+        if k:
+            assert np.abs(m["obj"][b, :k] - z["obj"][b, :k]).max() <= X_TOL
+
+
+def test_matcher_device_code_capacity_flags(match_emu):
+    """More roots than max_roots: the warp reports the overflow flag and keeps the first max_roots roots; a
+    frame-set without blobs yields no points."""
+    z = load_golden("pipe_c8_m16")
+    full = match_emu(z["K"], z["R"], z["t"], z["blob_xy"][:2], z["blob_n"][:2])
+    small = match_emu(z["K"], z["R"], z["t"], z["blob_xy"][:2], z["blob_n"][:2], max_roots=8)
+    assert (small["flags"] != 0).all() and (small["n"] <= 8).all() and (full["flags"] == 0).all()
+    empty = match_emu(z["K"], z["R"], z["t"], z["blob_xy"][:1], np.zeros((1, 8), np.int32))
+    assert empty["n"][0] == 0
