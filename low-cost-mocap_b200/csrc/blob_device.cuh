@@ -34,10 +34,14 @@ __device__ __forceinline__ uint32_t nibble_of(uint32_t hi) {
 }
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+#if defined(__CUDACC__)
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
+#else
+    return *p;                       // host-run checks of the device code (tests/hostcheck)
+#endif
 }
 
 __device__ __forceinline__ void append_segment(uint32_t* seg_count, uint32_t* seg_list, int max_segments,

@@ -71,6 +71,7 @@ __device__ __forceinline__ void finish_image(const FusedParams& P, unsigned char
     // ---- this warp finished the frame-set: match + triangulate --------------------------------
     __threadfence();                                   // acquire: blob lists of the other cameras
     const unsigned defer = __ldcg(&P.set_defer[set]);
+    __syncwarp();                                      // every lane has read the mark before lane 0 clears it
     if (lane == 0) { P.set_done[set] = 0; P.set_defer[set] = 0; }
     if (defer) {
         if (lane == 0) P.set_worklist[atomicAdd(P.set_work_count, 1u)] = (uint32_t)set;

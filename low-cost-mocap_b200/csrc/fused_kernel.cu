@@ -13,77 +13,7 @@
 // so the sparse stages hide under the HBM stream of the other warps of the SM instead of running as
 // separate kernels after it.  Images / frame-sets beyond the warp-level capacities are put on
 // worklists and finished by the full-size kernels (k_blob_reduce, k_match_triangulate) afterwards.
-#include "fused_common.cuh"
-
-#define FUSED_WARPS 8
-#define FUSED_UNROLL 6
-#define FUSED_SEGS_PER_ITER (32 * FUSED_UNROLL)      // 192 segments = 3 KB per warp iteration
-
-template <bool WIDE, bool USE_AND>
-__global__ void __launch_bounds__(FUSED_WARPS * 32, 4)
-k_pipeline_fused(const FusedParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* slab = smem_raw + P.slab_bytes * warp;
-
-    while (true) {
-        unsigned long long u = 0;
-        if (lane == 0) u = atomicAdd(P.unit_counter, 1ull);
-        u = __shfl_sync(0xffffffffu, u, 0);
-        if (u >= (unsigned long long)P.total_units) break;
-        const int img = (int)(u / P.units_per_image);
-        const int unit = (int)(u - (unsigned long long)img * P.units_per_image);
-
-        // ---- stream this slice of the image -----------------------------------------------------
-        const int s_begin = unit * P.iters_per_unit * FUSED_SEGS_PER_ITER;
-        const int s_end = min(P.seg_per_image, s_begin + P.iters_per_unit * FUSED_SEGS_PER_ITER);
-        const uint4* src = P.frames + (size_t)img * P.seg_per_image;
-        // rolling window: every lane keeps FUSED_UNROLL 128-bit loads in flight at all times -- an
-        // element is consumed and its register immediately re-armed with the load of the next
-        // iteration, so the warp never drains its memory pipeline between iterations.  Whole
-        // iterations run without bounds checks; a ragged end (seg_per_image % 256 != 0) is handled after.
-        const int n_full = (s_end - s_begin) / FUSED_SEGS_PER_ITER;
-        if (n_full > 0) {
-            const uint4* sp = src + s_begin + lane;
-            uint4 v[FUSED_UNROLL];
-#pragma unroll
-            for (int q = 0; q < FUSED_UNROLL; ++q) v[q] = ldg_stream(sp + q * 32);
-            for (int it = 0; it < n_full; ++it) {
-                const bool more = it + 1 < n_full;               // warp-uniform
-                const uint4* nx = sp + (it + 1) * FUSED_SEGS_PER_ITER;
-#pragma unroll
-                for (int q = 0; q < FUSED_UNROLL; ++q) {
-                    if (any_above<USE_AND>(v[q], P.tc)) {         // rare: a marker crosses these 16 pixels
-                        const uint32_t h0 = swar_gt(v[q].x, P.tc), h1 = swar_gt(v[q].y, P.tc);
-                        const uint32_t h2 = swar_gt(v[q].z, P.tc), h3 = swar_gt(v[q].w, P.tc);
-                        const int si = s_begin + it * FUSED_SEGS_PER_ITER + q * 32 + lane;
-                        const uint32_t m = nibble_of(h0) | (nibble_of(h1) << 4) | (nibble_of(h2) << 8) | (nibble_of(h3) << 12);
-                        const uint32_t slot = atomicAdd(&P.seg_count[img], 1u);
-                        if (slot < (uint32_t)P.E) P.seg_list[(size_t)img * P.E + slot] = ((uint32_t)si << 16) | m;
-                    }
-                    if (more) v[q] = ldg_stream(nx + q * 32);     // re-arm this slot at once
-                }
-            }
-        }
-        for (int si = s_begin + n_full * FUSED_SEGS_PER_ITER + lane; si < s_end; si += 32) {      // ragged end
-            const uint4 x = ldg_stream(src + si);
-            if (!any_above<USE_AND>(x, P.tc)) continue;
-            const uint32_t h0 = swar_gt(x.x, P.tc), h1 = swar_gt(x.y, P.tc);
-            const uint32_t h2 = swar_gt(x.z, P.tc), h3 = swar_gt(x.w, P.tc);
-            const uint32_t m = nibble_of(h0) | (nibble_of(h1) << 4) | (nibble_of(h2) << 8) | (nibble_of(h3) << 12);
-            const uint32_t slot = atomicAdd(&P.seg_count[img], 1u);
-            if (slot < (uint32_t)P.E) P.seg_list[(size_t)img * P.E + slot] = ((uint32_t)si << 16) | m;
-        }
-        __threadfence();                                   // release: this warp's list entries
-        __syncwarp();
-        unsigned done = 0;
-        if (lane == 0) done = atomicAdd(&P.img_done[img], 1u);
-        done = __shfl_sync(0xffffffffu, done, 0);
-        if (done != (unsigned)P.units_per_image - 1) continue;
-
-        finish_image<WIDE>(P, slab, img, lane);
-    }
-}
+#include "fused_device.cuh"
 
 size_t fused_slab_bytes(const mocap_config& c) {
     size_t a = sizeof(WarpSlab), b = warp_state_bytes(c.max_roots, c.n_cam, c.max_cands);

@@ -9,6 +9,9 @@
 #include <string.h>
 #include <atomic>
 #include <barrier>
+#include <chrono>
+#include <stdio.h>
+#include <stdlib.h>
 #include <functional>
 #include <memory>
 #include <thread>
@@ -30,14 +33,18 @@ struct Block {
 };
 struct Tid { unsigned x, y, z; };
 inline thread_local Tid tid{0, 0, 0};
+// SIMT_TRACE=1 in the environment: a watchdog prints, for a launch that has not finished after 20 s, which
+// rendezvous every thread last entered (a deadlock in emulated code is a divergent barrier in the device code)
+inline const char* volatile last_op[4096];
+inline const char* volatile last_where[4096];
 inline thread_local Block* blk = nullptr;
 
-inline void warp_sync() { blk->warp[tid.x >> 5]->arrive_and_wait(); }
+inline void warp_sync(const char* what = "warp_sync") { last_op[tid.x] = what; blk->warp[tid.x >> 5]->arrive_and_wait(); last_op[tid.x] = "running"; }
 inline unsigned long long exchange(unsigned long long v, int src_lane) {      // value of lane src_lane of my warp
     blk->xchg[tid.x] = v;
-    warp_sync();
+    warp_sync("shuffle");
     const unsigned long long r = blk->xchg[(tid.x & ~31u) + (unsigned)src_lane];
-    warp_sync();
+    warp_sync("shuffle (2)");
     return r;
 }
 
@@ -45,57 +52,83 @@ inline unsigned long long exchange(unsigned long long v, int src_lane) {      //
 inline void launch(int nt, const std::function<void()>& fn) {
     Block b(nt);
     std::vector<std::thread> th;
+    std::atomic<int> running{nt};
     for (int t = 0; t < nt; ++t)
-        th.emplace_back([&, t] { tid = Tid{(unsigned)t, 0, 0}; blk = &b; fn(); });
+        th.emplace_back([&, t] { tid = Tid{(unsigned)t, 0, 0}; blk = &b; last_op[t] = "running"; fn(); last_op[t] = "exited"; --running; });
+    std::thread watchdog;
+    if (getenv("SIMT_TRACE"))
+        watchdog = std::thread([&] {
+            for (int s = 0; s < 200 && running.load() > 0; ++s) std::this_thread::sleep_for(std::chrono::milliseconds(100));
+            if (running.load() > 0)
+                for (int t = 0; t < nt; ++t) fprintf(stderr, "simt: thread %d (warp %d lane %d): %s at %s\n", t, t >> 5, t & 31, last_op[t], last_where[t] ? last_where[t] : "?");
+        });
     for (auto& t : th) t.join();
+    if (watchdog.joinable()) watchdog.join();
 }
 
 }  // namespace simt
 
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
 #ifndef __noinline__
 #define __noinline__ __attribute__((noinline))
 #endif
 
 // ---- what the device headers call ------------------------------------------------------------------------
 #define threadIdx (simt::tid)
-inline void __syncthreads() { simt::blk->cta.arrive_and_wait(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_sync(); }
+inline void simt_syncthreads(const char* where) { simt::last_where[simt::tid.x] = where; simt::last_op[simt::tid.x] = "__syncthreads"; simt::blk->cta.arrive_and_wait(); simt::last_op[simt::tid.x] = "running"; }
+inline void simt_syncwarp(const char* where) { simt::last_where[simt::tid.x] = where; simt::warp_sync("__syncwarp"); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
-template <typename T> inline T __shfl_sync(unsigned, T v, int src) {
+template <typename T> inline T simt_shfl(T v, int src, const char* where) {
+    simt::last_where[simt::tid.x] = where;
     static_assert(sizeof(T) <= 8, "shuffle width");
     unsigned long long raw = 0; memcpy(&raw, &v, sizeof(T));
     raw = simt::exchange(raw, src & 31);
     T r; memcpy(&r, &raw, sizeof(T)); return r;
 }
-template <typename T> inline T __shfl_up_sync(unsigned m, T v, unsigned d) {
+template <typename T> inline T simt_shfl_up(T v, unsigned d, const char* where) {
     const int lane = (int)(simt::tid.x & 31);
-    const T r = __shfl_sync(m, v, lane >= (int)d ? lane - (int)d : lane);
-    return r;
+    return simt_shfl(v, lane >= (int)d ? lane - (int)d : lane, where);
 }
-template <typename T> inline T __shfl_down_sync(unsigned m, T v, unsigned d) {
+template <typename T> inline T simt_shfl_down(T v, unsigned d, const char* where) {
     const int lane = (int)(simt::tid.x & 31);
-    return __shfl_sync(m, v, lane + (int)d < 32 ? lane + (int)d : lane);
+    return simt_shfl(v, lane + (int)d < 32 ? lane + (int)d : lane, where);
 }
-template <typename T> inline T __shfl_xor_sync(unsigned m, T v, int x) { return __shfl_sync(m, v, (int)(simt::tid.x & 31) ^ x); }
-inline unsigned __ballot_sync(unsigned, int pred) {
+template <typename T> inline T simt_shfl_xor(T v, int x, const char* where) { return simt_shfl(v, (int)(simt::tid.x & 31) ^ x, where); }
+inline unsigned simt_ballot(int pred, const char* where) {
+    simt::last_where[simt::tid.x] = where;
     simt::blk->xchg[simt::tid.x] = pred ? 1ull : 0ull;
-    simt::warp_sync();
+    simt::warp_sync("ballot");
     unsigned r = 0;
     const unsigned base = simt::tid.x & ~31u;
     for (unsigned l = 0; l < 32 && base + l < (unsigned)simt::blk->nt; ++l) r |= (unsigned)simt::blk->xchg[base + l] << l;
     simt::warp_sync();
     return r;
 }
-inline unsigned __match_any_sync(unsigned, unsigned v) {
+inline unsigned simt_match_any(unsigned v, const char* where) {
+    simt::last_where[simt::tid.x] = where;
     simt::blk->xchg[simt::tid.x] = v;
-    simt::warp_sync();
+    simt::warp_sync("match_any");
     unsigned r = 0;
     const unsigned base = simt::tid.x & ~31u;
     for (unsigned l = 0; l < 32 && base + l < (unsigned)simt::blk->nt; ++l) r |= (simt::blk->xchg[base + l] == v ? 1u : 0u) << l;
     simt::warp_sync();
     return r;
 }
+#define SIMT_STR2(x) #x
+#define SIMT_STR(x) SIMT_STR2(x)
+#define SIMT_HERE __FILE__ ":" SIMT_STR(__LINE__)
+#define __syncthreads() simt_syncthreads(SIMT_HERE)
+#define __syncwarp(...) simt_syncwarp(SIMT_HERE)
+#define __shfl_sync(m, v, s) simt_shfl((v), (s), SIMT_HERE)
+#define __shfl_up_sync(m, v, d) simt_shfl_up((v), (d), SIMT_HERE)
+#define __shfl_down_sync(m, v, d) simt_shfl_down((v), (d), SIMT_HERE)
+#define __shfl_xor_sync(m, v, x) simt_shfl_xor((v), (x), SIMT_HERE)
+#define __ballot_sync(m, p) simt_ballot((p), SIMT_HERE)
+#define __match_any_sync(m, v) simt_match_any((v), SIMT_HERE)
+
 inline long long __double_as_longlong(double d) { long long r; memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
 inline int __float_as_int(float f) { int r; memcpy(&r, &f, 4); return r; }
