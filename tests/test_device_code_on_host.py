@@ -303,3 +303,26 @@ def test_single_pass_kernel_on_host_defers_what_a_warp_cannot_hold(fused_emu):
     for b in (0, 1, 3, 4, 5):
         k = d["n"][b]
         assert k == z["nroot"][b] and np.abs(d["obj"][b, :k] - z["obj"][b, :k]).max() <= X_TOL
+
+
+def test_single_pass_kernel_has_no_unintended_data_races(tmp_path):
+    """ThreadSanitizer over the emulated kernel: every CUDA thread is a host thread, so a missing barrier or
+    fence between warps (or lanes) is a reportable data race.  The union-find of the blob reduce races BY DESIGN
+    (lock-free path halving + atomicMin, blob_device.cuh) and is suppressed; nothing else may be reported, on
+    light frame-sets and on the deferral path."""
+    import shutil
+    tsan = subprocess.run(["gcc", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    if not tsan or not os.path.isabs(tsan) or not os.path.exists(tsan):
+        pytest.skip("libtsan not available")
+    lib = str(tmp_path / "libfused_tsan.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-shared", "-fPIC", "-pthread", "-I" + CUDA_INC,
+                           "-Wno-attributes", "-Wno-tsan", "-fno-strict-aliasing", "-o", lib, os.path.join(HC, "fused_emu_host.cpp")])
+    supp = tmp_path / "supp.txt"
+    supp.write_text("race:uf_find\nrace:uf_unite\nrace:atomicMin\n")
+    env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS=f"report_signal_unsafe=0 history_size=4 exitcode=0 suppressions={supp}")
+    for extra in ([], ["crowded"]):
+        r = subprocess.run([shutil.which("python") or "python", os.path.join(HC, "tsan_fused_run.py"), ROOT, lib, "pipe_c4_m4"] + extra,
+                           capture_output=True, text=True, env=env, timeout=280)
+        out = r.stdout + r.stderr
+        assert "RESULT 0" in out, out[-2000:]
+        assert "WARNING: ThreadSanitizer" not in out, out[:4000]
