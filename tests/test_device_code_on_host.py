@@ -326,3 +326,70 @@ def test_single_pass_kernel_has_no_unintended_data_races(tmp_path):
         out = r.stdout + r.stderr
         assert "RESULT 0" in out, out[-2000:]
         assert "WARNING: ThreadSanitizer" not in out, out[:4000]
+
+
+def test_blob_device_code_fuzz_vs_cv2(blob_emu):
+    """Random solid shapes (random walks of squares, filled; touching, on the border, in images as small as 16x2)
+    through both variants of the blob code: centres, count and order identical to cv2's findContours + moments."""
+    import cv2
+    from oracle.ref_port import RefPort
+    port = RefPort([np.eye(3)])
+    rng = np.random.default_rng(11)
+    done = blobs = 0
+    while done < 150:
+        W = int(rng.choice([16, 32, 48, 64, 160, 320])); H = int(rng.integers(2, 160))
+        img = np.zeros((H, W), np.uint8)
+        for _ in range(int(rng.integers(0, 10))):
+            y, x, r = int(rng.integers(0, H)), int(rng.integers(0, W)), int(rng.integers(0, 3))
+            for _ in range(int(rng.integers(1, 50))):
+                img[max(0, y - r):y + r + 1, max(0, x - r):x + r + 1] = 255
+                y = int(np.clip(y + rng.integers(-2, 3), 0, H - 1)); x = int(np.clip(x + rng.integers(-2, 3), 0, W - 1))
+        contours, _ = cv2.findContours(img, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
+        cv2.drawContours(img, contours, -1, 255, thickness=cv2.FILLED)
+        _, hier = cv2.findContours(img, cv2.RETR_CCOMP, cv2.CHAIN_APPROX_NONE)
+        if hier is not None and (hier[0][:, 3] >= 0).any():
+            continue                                          # a hole survived: outside the S1 contract (DESIGN.md section 7)
+        grey = (img > 0).astype(np.uint8) * int(rng.integers(60, 256))
+        ref = [q for q in port.find_dot(np.repeat(grey[:, :, None], 3, axis=2)) if q[0] is not None]
+        for force_cta in (0, 1):
+            d = blob_emu(grey, E=4096, force_cta=force_cta, seed=done)
+            assert d["xy"].tolist() == ref[:64], (done, W, H, force_cta)
+        blobs += len(ref)
+        done += 1
+    assert blobs > 300
+
+
+def test_matcher_device_code_fuzz_vs_oracle(match_emu):
+    """Random blob constellations that do not come from any scene (many wrong correspondences, ragged counts,
+    near-threshold distances to epipolar lines): kept roots, their order and the chosen points equal the oracle's."""
+    import importlib
+    from oracle.ref_port import RefPort
+    synth = importlib.import_module("low-cost-mocap_b200.synth")
+    rng = np.random.default_rng(78)
+    for C in (3, 5):
+        poses, K = synth.make_rig(C)
+        port = RefPort([K] * C)
+        B, MB = 25, 16
+        xy = np.zeros((B, C, MB, 2), np.int32); n = np.zeros((B, C), np.int32)
+        for b in range(B):
+            pts3 = rng.uniform(-0.5, 0.5, size=(int(rng.integers(0, 5)), 3)) + np.array([0, 0, 3.0])
+            for c in range(C):
+                lst = [list(map(int, synth.project(p[None], poses[c], K)[0])) for p in pts3 if rng.uniform() < 0.85]
+                lst += [[int(rng.integers(100, 540)), int(rng.integers(100, 380))] for _ in range(int(rng.integers(0, 4)))]
+                uniq = [list(q) for q in dict.fromkeys(tuple(q) for q in lst)]
+                uniq = [uniq[i] for i in rng.permutation(len(uniq))][:MB]
+                n[b, c] = len(uniq)
+                if uniq:
+                    xy[b, c, :len(uniq)] = uniq
+        R = np.stack([np.asarray(p["R"], dtype=np.float64) for p in poses]); t = np.stack([np.asarray(p["t"], dtype=np.float64).reshape(3) for p in poses])
+        d = match_emu(K, R, t, xy, n, max_roots=64, max_cands=16)
+        assert not d["flags"].any()
+        for b in range(B):
+            lists = [[list(map(int, xy[b, c, i])) for i in range(n[b, c])] for c in range(C)]
+            e, o, _ = port.match_and_triangulate(lists, poses)
+            assert d["n"][b] == len(e), (C, b)
+            if len(e):
+                ref = np.asarray(o, dtype=np.float64)
+                scale = np.maximum(1.0, np.abs(ref).max(axis=1, keepdims=True))      # wrong correspondences are ill-conditioned
+                assert (np.abs(d["obj"][b, :len(e)] - ref) / scale).max() <= 1e-6, (C, b)
+                assert np.allclose(d["err"][b, :len(e)], e, rtol=1e-6, atol=1e-9)
