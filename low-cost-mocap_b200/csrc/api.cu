@@ -104,11 +104,12 @@ int mocap_create(mocap_ctx** out, const mocap_config* cfg) {
         if ((st = blob_kernels_init(ctx)) != MOCAP_OK) break;
         if ((st = match_kernels_init(ctx)) != MOCAP_OK) break;
         {
-            // MOCAP_PIPELINE = split | fused | tma pins the pipeline (A/B measurements); unset: single-pass kernel,
+            // MOCAP_PIPELINE = split | fused | phased | tma pins the pipeline (A/B measurements); unset: single-pass kernel,
             // except for batches of heavy frame-sets (see pick_fused)
             const char* mode = getenv("MOCAP_PIPELINE");
             ctx->use_fused = (mode && strcmp(mode, "split") == 0) ? 0 : 1;
             ctx->use_tma = (mode && strcmp(mode, "tma") == 0) ? 1 : 0;
+            ctx->use_phased = (mode && strcmp(mode, "phased") == 0) ? 1 : 0;
             ctx->pipeline_auto = (mode && mode[0]) ? 0 : 1;
         }
         {

@@ -48,6 +48,7 @@ struct mocap_ctx {
     int       fused_ctas_per_sm;
     int       tma_ctas_per_sm;   // 0: bulk-copy kernel unavailable for this configuration
     int       use_tma;           // MOCAP_PIPELINE=tma: stream through the bulk-copy ring kernel
+    int       use_phased;        // MOCAP_PIPELINE=phased: phase-synchronous variant of the single-pass kernel (opt-in, fused_phased.cuh)
     int       pipeline_auto;     // MOCAP_PIPELINE unset: heavy batches (many blobs per frame-set) take the three-kernel pipeline
     unsigned long long* d_stat_acc;                  // device accumulator of the blob statistic
     volatile unsigned long long* h_stat;             // pinned, mapped: {blobs, images} of the last batch, written by the GPU

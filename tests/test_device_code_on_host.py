@@ -215,7 +215,7 @@ def fused_emu():
                            "-fno-strict-aliasing", "-o", out, src])
     lib = ctypes.CDLL(out)
 
-    def run(frames, K, R, t, threshold=51, max_blobs=64, E=1024, max_roots=128, max_cands=8, max_groups=4096, n_warps=8, runs=2):
+    def run(frames, K, R, t, threshold=51, max_blobs=64, E=1024, max_roots=128, max_cands=8, max_groups=4096, n_warps=8, runs=2, phased=0):
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         B, C, H, W = frames.shape
         K = np.ascontiguousarray(np.stack([K] * C) if np.ndim(K) == 2 else K, dtype=np.float64)
@@ -225,7 +225,7 @@ def fused_emu():
         iw = np.zeros(B * C, np.uint32); sw = np.zeros(B, np.uint32); cnt = np.zeros(4, np.int64)
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         rc = lib.hc_pipeline_fused(p(frames), B, C, W, H, int(threshold), p(K), p(R), p(t), max_blobs, E, max_roots, max_cands,
-                                   ctypes.c_uint(max_groups), n_warps, runs, p(obj), p(err), p(k), p(fl), p(bxy), p(bn), p(iw), p(sw), p(cnt))
+                                   ctypes.c_uint(max_groups), n_warps, runs, phased, p(obj), p(err), p(k), p(fl), p(bxy), p(bn), p(iw), p(sw), p(cnt))
         assert rc == 0
         return {"obj": obj, "err": err, "n": k, "flags": fl, "blob_xy": bxy.reshape(B, C, max_blobs, 2), "blob_n": bn.reshape(B, C),
                 "deferred_images": iw[:cnt[0]].tolist(), "deferred_sets": sw[:cnt[1]].tolist(), "dirty_scratch": int(cnt[2])}
@@ -320,7 +320,7 @@ def test_single_pass_kernel_has_no_unintended_data_races(tmp_path):
     supp = tmp_path / "supp.txt"
     supp.write_text("race:uf_find\nrace:uf_unite\nrace:atomicMin\n")
     env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS=f"report_signal_unsafe=0 history_size=4 exitcode=0 suppressions={supp}")
-    for extra in ([], ["crowded"]):
+    for extra in ([], ["crowded"], ["phased"], ["phased", "crowded"]):
         r = subprocess.run([shutil.which("python") or "python", os.path.join(HC, "tsan_fused_run.py"), ROOT, lib, "pipe_c4_m4"] + extra,
                            capture_output=True, text=True, env=env, timeout=280)
         out = r.stdout + r.stderr
@@ -393,3 +393,58 @@ def test_matcher_device_code_fuzz_vs_oracle(match_emu):
                 scale = np.maximum(1.0, np.abs(ref).max(axis=1, keepdims=True))      # wrong correspondences are ill-conditioned
                 assert (np.abs(d["obj"][b, :len(e)] - ref) / scale).max() <= 1e-6, (C, b)
                 assert np.allclose(d["err"][b, :len(e)], e, rtol=1e-6, atol=1e-9)
+
+
+# ------------------------------------------------- the phase-synchronous variant (MOCAP_PIPELINE=phased, opt-in)
+@pytest.mark.parametrize("name", PIPE_CASES)
+def test_phased_kernel_on_host_vs_reference_golden(fused_emu, name):
+    """k_pipeline_phased (csrc/fused_phased.cuh): images and frame-sets are queued per CTA and the CTA changes
+    phase as a whole.  Same golden results as the single-pass kernel, every counter re-armed after a run."""
+    z = load_golden(name)
+    B = 12 if name != "pipe_c8_m16" else 6
+    d = fused_emu(z["frames"][:B], z["K"], z["R"], z["t"], runs=2, phased=1)
+    assert d["deferred_images"] == [] and d["deferred_sets"] == [] and d["dirty_scratch"] == 0
+    assert np.array_equal(d["blob_n"], z["blob_n"][:B])
+    assert np.array_equal(d["n"], z["nroot"][:B]) and not d["flags"].any()
+    for b in range(B):
+        for c in range(d["blob_n"].shape[1]):
+            k = d["blob_n"][b, c]
+            assert np.array_equal(d["blob_xy"][b, c, :k], z["blob_xy"][b, c, :k])
+        k = d["n"][b]
+        if k:
+            assert np.abs(d["obj"][b, :k] - z["obj"][b, :k]).max() <= X_TOL
+            assert np.allclose(d["err"][b, :k], z["err"][b, :k], rtol=ERR_RTOL, atol=1e-12)
+
+
+def test_phased_kernel_on_host_equals_single_pass_kernel(fused_emu):
+    """Bit-identical outputs of the two kernels on ragged geometry, many small frame-sets (the queues wrap several
+    times) and a crowded image (deferral to the worklists)."""
+    rng = np.random.default_rng(5)
+    W, H, C, B = 48, 32, 3, 40
+    frames = rng.integers(0, 40, size=(B, C, H, W), dtype=np.uint8)
+    yy, xx = np.mgrid[:H, :W]
+    for b in range(B):
+        for c in range(C):
+            for _ in range(3):
+                cy, cx, sg = rng.uniform(3, H - 3), rng.uniform(3, W - 3), rng.uniform(0.8, 1.8)
+                frames[b, c] = np.maximum(frames[b, c], (255 * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * sg * sg))).astype(np.uint8))
+    K = np.array([[W * 1.0, 0, W / 2.0], [0, W * 1.0, H / 2.0], [0, 0, 1]])
+    R = np.stack([np.eye(3)] * C); t = np.array([[-0.3 * c, 0.0, 0.0] for c in range(C)])
+    a = fused_emu(frames, K, R, t, max_roots=32, runs=2, phased=0)
+    b = fused_emu(frames, K, R, t, max_roots=32, runs=2, phased=1)
+    assert b["dirty_scratch"] == 0 and b["deferred_images"] == [] and b["deferred_sets"] == []
+    assert np.array_equal(a["blob_n"], b["blob_n"]) and np.array_equal(a["blob_xy"], b["blob_xy"])
+    assert np.array_equal(a["n"], b["n"]) and np.array_equal(a["flags"], b["flags"])
+    for s in range(B):
+        k = a["n"][s]
+        assert np.array_equal(a["obj"][s, :k], b["obj"][s, :k]) and np.array_equal(a["err"][s, :k], b["err"][s, :k])
+    z = load_golden("pipe_c4_m4")
+    crowded = z["frames"][:6].copy()
+    for k in range(70):
+        y, x = 10 + 6 * (k // 35), 20 + 16 * (k % 35)
+        crowded[2, 1, y:y + 3, x:x + 3] = 255
+    d = fused_emu(crowded, z["K"], z["R"], z["t"], runs=1, phased=1)
+    assert d["deferred_images"] == [2 * 4 + 1] and d["deferred_sets"] == [2] and d["dirty_scratch"] == 0
+    for s in (0, 1, 3, 4, 5):
+        k = d["n"][s]
+        assert k == z["nroot"][s] and np.abs(d["obj"][s, :k] - z["obj"][s, :k]).max() <= X_TOL

@@ -1013,3 +1013,26 @@ def test_heavy_batches_take_the_three_kernel_pipeline(torch, monkeypatch):
             for b in range(len(n)):
                 assert np.array_equal(o["obj"][b, :n[b]], outs[0]["obj"][b, :n[b]])
                 assert np.array_equal(o["err"][b, :n[b]], outs[0]["err"][b, :n[b]])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MOCAP_TEST_PHASED") != "1",
+                    reason="phase-synchronous variant of the single-pass kernel: opt-in until it has been measured (MOCAP_TEST_PHASED=1)")
+@pytest.mark.parametrize("name", PIPE_CASES)
+def test_phased_pipeline_agrees_with_fused(torch, monkeypatch, name):
+    """MOCAP_PIPELINE=phased against the default single-pass kernel: identical bits, twice on the same context."""
+    z = load_golden(name)
+    C = int(z["C"])
+    results = {}
+    for mode in ("fused", "phased"):
+        monkeypatch.setenv("MOCAP_PIPELINE", mode)
+        ctx = _ctx(C, max_blobs=64, max_roots=128)
+        ctx.set_cameras([z["K"]] * C, poses_from(z))
+        for _ in range(2):
+            out = ctx.pipeline(torch.from_numpy(z["frames"]).cuda())
+            torch.cuda.synchronize()
+        results[mode] = {k: v.cpu().numpy().copy() for k, v in out.items()}
+    n = results["fused"]["n"]
+    assert np.array_equal(results["phased"]["n"], n) and np.array_equal(n, z["nroot"])
+    for b in range(len(n)):
+        assert np.array_equal(results["phased"]["obj"][b, :n[b]], results["fused"]["obj"][b, :n[b]])
+        assert np.array_equal(results["phased"]["err"][b, :n[b]], results["fused"]["err"][b, :n[b]])
