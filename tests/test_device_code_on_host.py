@@ -305,7 +305,7 @@ def test_single_pass_kernel_on_host_defers_what_a_warp_cannot_hold(fused_emu):
         assert k == z["nroot"][b] and np.abs(d["obj"][b, :k] - z["obj"][b, :k]).max() <= X_TOL
 
 
-def test_single_pass_kernel_has_no_unintended_data_races(tmp_path):
+def test_device_code_has_no_unintended_data_races(tmp_path):
     """ThreadSanitizer over the emulated kernel: every CUDA thread is a host thread, so a missing barrier or
     fence between warps (or lanes) is a reportable data race.  The union-find of the blob reduce races BY DESIGN
     (lock-free path halving + atomicMin, blob_device.cuh) and is suppressed; nothing else may be reported, on
@@ -314,9 +314,12 @@ def test_single_pass_kernel_has_no_unintended_data_races(tmp_path):
     tsan = subprocess.run(["gcc", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
     if not tsan or not os.path.isabs(tsan) or not os.path.exists(tsan):
         pytest.skip("libtsan not available")
-    lib = str(tmp_path / "libfused_tsan.so")
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-shared", "-fPIC", "-pthread", "-I" + CUDA_INC,
-                           "-Wno-attributes", "-Wno-tsan", "-fno-strict-aliasing", "-o", lib, os.path.join(HC, "fused_emu_host.cpp")])
+    libs = {}
+    for name in ("fused", "blob", "match"):
+        libs[name] = str(tmp_path / f"lib{name}_tsan.so")
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-shared", "-fPIC", "-pthread", "-I" + CUDA_INC,
+                               "-Wno-attributes", "-Wno-tsan", "-fno-strict-aliasing", "-o", libs[name], os.path.join(HC, f"{name}_emu_host.cpp")])
+    lib = libs["fused"]
     supp = tmp_path / "supp.txt"
     supp.write_text("race:uf_find\nrace:uf_unite\nrace:atomicMin\n")
     env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS=f"report_signal_unsafe=0 history_size=4 exitcode=0 suppressions={supp}")
@@ -326,6 +329,12 @@ def test_single_pass_kernel_has_no_unintended_data_races(tmp_path):
         out = r.stdout + r.stderr
         assert "RESULT 0" in out, out[-2000:]
         assert "WARNING: ThreadSanitizer" not in out, out[:4000]
+    # the blob code on its own (one-warp and 128-thread variants, light and crowded image) and the matcher
+    r = subprocess.run([shutil.which("python") or "python", os.path.join(HC, "tsan_blob_match_run.py"), ROOT, libs["blob"], libs["match"]],
+                       capture_output=True, text=True, env=env, timeout=280)
+    out = r.stdout + r.stderr
+    assert out.count("BLOB") == 4 and "MATCH True" in out, out[-2000:]
+    assert "WARNING: ThreadSanitizer" not in out, out[:4000]
 
 
 def test_blob_device_code_fuzz_vs_cv2(blob_emu):
