@@ -21,10 +21,17 @@ this box's host cores on a bounded sample.
 Python and /root/reference does not exist on the GPU box) on all host cores, same workload
 shape, bounded sample per step.
 """
+import os
+
+# one worker PROCESS per host core is how the CPU arm fans out; BLAS / OpenMP / cv2 pools inside every worker
+# would oversubscribe the box 128-fold, so they are pinned to one thread before numpy / scipy / cv2 are imported
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS", "VECLIB_MAXIMUM_THREADS"):
+    os.environ[_v] = "1"
+
 import argparse
 import importlib
 import json
-import os
+import math
 import subprocess
 import sys
 import threading
@@ -104,30 +111,82 @@ _W = {}
 def _cpu_init(K, poses):
     import cv2
     cv2.setNumThreads(1)
-    try:                                   # one worker per core: keep BLAS/OpenMP pools from oversubscribing
-        from threadpoolctl import threadpool_limits
-        _W["limit"] = threadpool_limits(1)
-    except Exception:
-        pass
     from oracle.ref_port import RefPort
     _W["port"] = RefPort([K] * len(poses))
     _W["poses"] = poses
 
 
-def _cpu_one(index):
-    # frames are inherited through fork (_W["frames"] is set before the pool starts): tasks carry
-    # an index only, so no image bytes travel through pipes
-    port, poses, frames = _W["port"], _W["poses"], _W["frames"]
-    frame_set = frames[index % len(frames)]
-    pts = [port.find_dot(np.repeat(img[:, :, None], 3, axis=2)) for img in frame_set]
-    e, o, _ = port.match_and_triangulate(pts, poses)
-    return len(e)
+def _cpu_range(rng):
+    """One task = one contiguous range of frame-sets (a handful of tasks per worker, so the dispatcher thread is
+    idle).  Frames are inherited through fork as H x W x 3 arrays -- the layout the reference's _find_dot receives
+    (helpers.py:143) -- so tasks carry two integers and no image bytes travel through pipes."""
+    port, poses, frames3 = _W["port"], _W["poses"], _W["frames3"]
+    lo, hi = rng
+    got = 0
+    for index in range(lo, hi):
+        frame_set = frames3[index % len(frames3)]
+        pts = [port.find_dot(img) for img in frame_set]
+        e, o, _ = port.match_and_triangulate(pts, poses)
+        got += len(e)
+    return got
 
 
-def cpu_pass(pool_obj, frames, n_sets):
+def cpu_pass(pool_obj, n_sets, n_workers):
+    n_tasks = min(n_sets, 4 * n_workers)
+    edges = [round(i * n_sets / n_tasks) for i in range(n_tasks + 1)]
+    tasks = [(edges[i], edges[i + 1]) for i in range(n_tasks) if edges[i + 1] > edges[i]]
     t0 = time.perf_counter()
-    got = pool_obj.map(_cpu_one, range(n_sets), chunksize=max(1, n_sets // (8 * pool_obj._processes)))
+    got = pool_obj.map(_cpu_range, tasks, chunksize=1)
     return time.perf_counter() - t0, sum(got)
+
+
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+class CpuArm:
+    """The reference's CPU path (oracle port: the reference's own cv2 / numpy / scipy call sequence, pinned
+    bit-exact to it) fanned out over the host cores.  The SAME object times the GPU arm's cpu_baseline leg and
+    the --impl reference arm, so the two agree."""
+
+    def __init__(self, frames, K, poses):
+        import multiprocessing as mp
+        self.cores = host_cores()
+        self.K, self.poses = K, poses
+        # 3-channel frames as the reference's capture loop hands them to _find_dot; built once, outside every timed region
+        n3 = min(len(frames), 256 if frames.shape[1] <= 4 else 96)
+        _W["frames3"] = np.ascontiguousarray(np.repeat(frames[:n3, :, :, :, None], 3, axis=4))
+        _cpu_init(K, poses)
+        t0 = time.perf_counter()                       # single core first (the reference is single-threaded Python)
+        n = 0
+        while time.perf_counter() - t0 < 3.0:
+            _cpu_range((n, n + 1))
+            n += 1
+        self.single_core = n / (time.perf_counter() - t0)
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(K, poses))
+        cpu_pass(self.pool, 2 * self.cores, self.cores)        # spin the workers up (imports, page tables)
+        t, _ = cpu_pass(self.pool, 4 * self.cores, self.cores)
+        self.rate_probe = 4 * self.cores / t
+
+    def sample_for(self, seconds, batch):
+        """frame-sets per pass: at least 64 per worker so that start-up and the tail are amortised"""
+        return int(min(max(batch, 64 * self.cores), max(64 * self.cores, seconds * self.rate_probe)))
+
+    def run(self, n_sets):
+        t, _ = cpu_pass(self.pool, n_sets, self.cores)
+        return t
+
+    def report(self, value, sample_text):
+        eff = value / (self.cores * self.single_core)
+        if eff < 0.5:
+            print(f"bench.py: WARNING: CPU arm parallel efficiency {eff:.2f} < 0.5 ({value:.0f} frame-sets/s on {self.cores} "
+                  f"cores vs {self.single_core:.0f} on one): the CPU figure understates the box", file=sys.stderr, flush=True)
+        return {"value": value, "unit": "frame-sets/s", "cores": self.cores, "kind": "port", "sample": sample_text,
+                "single_core_value": self.single_core, "parallel_efficiency": eff}
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def oracle_tracks(frames, world, n_check=8):
@@ -158,28 +217,22 @@ def compare_with_oracle(ref, out):
 
 
 def run_reference_arm(args):
-    import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     frames, truth, poses, K = make_pool()
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    _W["frames"] = frames
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(K, poses)) as pool_obj:
-        # size one step so that the whole run (K timed steps + W quarter-size warm-up steps) takes about two
-        # and a half minutes on this box, and no step more than ~4 s
-        cpu_pass(pool_obj, frames, cores * 2)                      # spin the workers up
-        t_probe, _ = cpu_pass(pool_obj, frames, cores * 2)
-        per_set = t_probe / (cores * 2)
-        step_s = min(4.0, max(0.25, 150.0 / (args.steps + 0.25 * args.warmup)))
-        sample = int(min(BATCH, max(cores * 4, step_s / per_set)))
-        for _ in range(args.warmup):
-            cpu_pass(pool_obj, frames, max(cores, sample // 4))
-        t = 0.0
-        for _ in range(args.steps):
-            dt, _ = cpu_pass(pool_obj, frames, sample)
-            t += dt
+    arm = CpuArm(frames, K, poses)
+    cores = arm.cores
+    # size one step so that the whole run (K timed steps + W quarter-size warm-up steps) takes about two and a
+    # half minutes on this box; never fewer than 64 frame-sets per worker (start-up and tail amortised)
+    step_s = max(0.25, 150.0 / (args.steps + 0.25 * args.warmup))
+    sample = arm.sample_for(step_s, BATCH)
+    for _ in range(args.warmup):
+        arm.run(max(16 * cores, sample // 4))
+    t = 0.0
+    for _ in range(args.steps):
+        t += arm.run(sample)
+    arm.close()
     value = sample * args.steps / t
     line = {
         "impl": "reference", "metric": f"mocap frame-sets/s ({N_CAM}-cam 640x480 synthetic, blob+epipolar+DLT)",
@@ -189,8 +242,7 @@ def run_reference_arm(args):
         "config": {"workload": f"BASELINE config {'2' if N_CAM == 4 else '3/4 shape'}: {N_CAM} cameras, {N_MARKERS} markers, 640x480 uint8 frame-sets; "
                                f"bounded sample of {sample} frame-sets per step of the {BATCH}-frame-set batch",
                    "cameras": N_CAM, "markers": N_MARKERS, "frame_sets_per_step": sample},
-        "cpu_baseline": {"value": value, "unit": "frame-sets/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} frame-sets per step x {args.steps} steps, one worker process per core"},
+        "cpu_baseline": arm.report(value, f"{sample} frame-sets per step x {args.steps} steps, one worker process per core"),
         "e2e": {"value": value, "unit": "frame-sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -216,24 +268,11 @@ def run_gpu_arm(args):
         # CPU baseline FIRST, before this process owns a CUDA context and 12 GB of pinned memory (forking
         # worker processes out of such a process is slow and unsafe): the oracle port on this box's host
         # cores, bounded sample of the same workload
-        import multiprocessing as mp
-        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        _W["frames"] = frames
-        mctx = mp.get_context("fork")
-        with mctx.Pool(cores, initializer=_cpu_init, initargs=(K, poses)) as pool_obj:
-            cpu_pass(pool_obj, frames, cores * 2)                  # spin the workers up
-            t_probe, _ = cpu_pass(pool_obj, frames, cores * 2)
-            sample = int(min(BATCH, max(cores * 4, 10.0 / (t_probe / (cores * 2)))))
-            t_cpu, _ = cpu_pass(pool_obj, frames, sample)
-        # the reference itself is single-threaded Python: one core, a few seconds, in this process
-        _cpu_init(K, poses)
-        t0 = time.perf_counter()
-        n_single = 0
-        while time.perf_counter() - t0 < 3.0:
-            _cpu_one(n_single)
-            n_single += 1
-        single_core = n_single / (time.perf_counter() - t0)
-        cpu_res = (cores, sample, t_cpu, single_core, oracle_tracks(frames, world))
+        arm = CpuArm(frames, K, poses)
+        sample = arm.sample_for(12.0, BATCH)
+        t_cpu = arm.run(sample)
+        arm.close()
+        cpu_res = (arm, sample, t_cpu, oracle_tracks(frames, world))
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -352,7 +391,7 @@ def run_gpu_arm(args):
         # step bytes * steps / launches (one launch per step for the fused kernel, three for the split pipeline)
         alg_bytes = bytes_per_step * args.steps / kern_n if kern_n else None
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
-        cores, sample, t_cpu, single_core, ref_tracks = cpu_res
+        arm, sample, t_cpu, ref_tracks = cpu_res
         parity = compare_with_oracle(ref_tracks, out)
         gpu_points = int(out["n"][:1].sum().item())
         line = {
@@ -373,9 +412,7 @@ def run_gpu_arm(args):
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes) if alg_bytes else None,
                          "avg_launch_ms": kern_ms, "launches_timed": kern_n,
                          "whole_step_frac": (bytes_per_step * args.steps / (ms_total * 1e-3) / 1e9) / peak},
-            "cpu_baseline": {"value": sample / t_cpu, "unit": "frame-sets/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} frame-sets of the same workload, one worker process per core",
-                             "single_core_value": single_core},
+            "cpu_baseline": arm.report(sample / t_cpu, f"{sample} frame-sets of the same workload, one worker process per core"),
             "parity_vs_oracle": parity,
             "clocks": clocks,
         }

@@ -25,6 +25,23 @@ from ._lib import MocapError, Config, BAOptions, BAReport, check
 
 THRESHOLD = 51   # cv.threshold(grey, 255*0.2, 255, THRESH_BINARY) on uint8 == pix > 51 (helpers.py:146)
 
+# MOCAP_F_* bits of include/mocap_b200.h
+F_SEGMENTS, F_BLOBS, F_ROOTS, F_CANDS, F_GROUPS = 1, 2, 4, 8, 16
+_FLAG_NAMES = {F_SEGMENTS: "max_segments", F_BLOBS: "max_blobs", F_ROOTS: "max_roots", F_CANDS: "max_cands",
+               F_GROUPS: "max_groups"}
+# the reference is unbounded; the drop-in mirrors run with the compile-time maxima and raise on overflow
+MIRROR_LIMITS = dict(max_blobs=64, max_segments=4096, max_roots=128, max_cands=16, max_groups=1 << 16)
+
+
+def raise_on_overflow(flags, what):
+    """The reference keeps every contour / root / candidate group; a result truncated at a configured
+    capacity would differ from it silently, so the mirrors turn any MOCAP_F_* bit into an error."""
+    flags = int(flags)
+    if flags:
+        names = [n for b, n in _FLAG_NAMES.items() if flags & b]
+        raise MocapError(-1, f"{what}: capacity overflow ({', '.join(names)}); results would be truncated "
+                             f"where the reference is unbounded")
+
 
 def _torch():
     import torch
@@ -388,7 +405,7 @@ class MocapSession:
         n = len(camera_poses)
         if n > len(self.intrinsics):
             raise ValueError("more camera poses than intrinsics")
-        c = self.ctx(n)
+        c = self.ctx(n, **MIRROR_LIMITS)
         c.set_cameras(self.intrinsics[:n], camera_poses)
         return c
 
@@ -405,9 +422,11 @@ def find_dot(img, session=None):
     with s._lock:
         ctx = s._ctxs.get(("detect", w, h))
         if ctx is None:
-            ctx = MocapContext(1, w, h, s.device)
+            ctx = MocapContext(1, w, h, s.device, max_blobs=MIRROR_LIMITS["max_blobs"],
+                               max_segments=MIRROR_LIMITS["max_segments"])
             s._ctxs[("detect", w, h)] = ctx
         d = ctx.detect(torch.from_numpy(img).to(ctx.torch_device))
+        raise_on_overflow(d["flags"][0].item(), "find_dot")
         n = int(d["n"][0].item())
         pts = d["xy"][0, :n].cpu().numpy().tolist()
     for x, y in pts:
@@ -483,6 +502,7 @@ def find_point_correspondance_and_object_points(image_points, camera_poses, fram
             if k:
                 xy[c, :k] = np.asarray(image_points[c], dtype=np.int32)
         d = ctx.match_triangulate(torch.from_numpy(xy).to(ctx.torch_device), torch.from_numpy(n).to(ctx.torch_device))
+        raise_on_overflow(d["flags"][0].item(), "find_point_correspondance_and_object_points")
         k = int(d["n"][0].item())
         errors = d["err"][0, :k].cpu().numpy()
         object_points = d["obj"][0, :k].cpu().numpy()
@@ -499,14 +519,14 @@ def locate_objects(object_points, errors, session=None):
     if K == 0:
         return []
     with s._lock:
-        ctx = s.ctx(len(s.intrinsics))
+        ctx = s.ctx(len(s.intrinsics), **MIRROR_LIMITS)
         R = ctx.cfg.max_roots
         if K > R:
             raise MocapError(-1, f"{K} points; context keeps {R}")
         obj = np.zeros((1, R, 3)); err = np.zeros((1, R))
         obj[0, :K] = pts; err[0, :K] = errs
         d = ctx.locate_objects(torch.from_numpy(obj).to(ctx.torch_device), torch.from_numpy(err).to(ctx.torch_device),
-                               torch.tensor([K], dtype=torch.int32, device=ctx.torch_device), max_objects=max(1, K // 3))
+                               torch.tensor([K], dtype=torch.int32, device=ctx.torch_device), max_objects=K)      # only i is screened: up to one object per point (helpers.py:433-436)
         k = int(d["n"][0].item())
         rec = d["objects"][0, :k].cpu().numpy()
         di = d["drone_index"][0, :k].cpu().numpy()
@@ -546,19 +566,39 @@ def calculate_camera_poses(image_points, socketio=None, session=None):
     return out
 
 
-def install_into(helpers_module, session=None):
-    """Point a loaded reference ``helpers`` module at the CUDA path."""
+PATCHED_NAMES = ("triangulate_point", "triangulate_points", "calculate_reprojection_error",
+                 "calculate_reprojection_errors", "find_point_correspondance_and_object_points",
+                 "bundle_adjustment", "locate_objects")
+
+
+def install_into(helpers_module, *also, session=None):
+    """Point a loaded reference ``helpers`` module at the CUDA path.
+
+    ``also``: modules that imported the hot-path names BY VALUE -- the reference's ``index.py`` does
+    (``from helpers import ... bundle_adjustment, triangulate_points, calculate_reprojection_errors``,
+    index.py:1), so ``calculate_camera_pose`` (index.py:254,272,274,275) would keep the CPU functions.
+    Every name of PATCHED_NAMES such a module holds is re-bound as well:
+    ``install_into(helpers, sys.modules[__name__])`` from inside index.py."""
     cams = helpers_module.Cameras.instance()
     s = session or MocapSession.install([np.asarray(p["intrinsic_matrix"], dtype=np.float64) for p in cams.camera_params])
     # helpers.Cameras is a Singleton WRAPPER object (Singleton.py:17-37); _camera_read looks _find_dot up on the
     # decorated class of the instance, so that is where the replacement goes
     type(cams)._find_dot = lambda self, img: find_dot(img, s)
-    helpers_module.triangulate_point = lambda ip, cp: triangulate_point(ip, cp, s)
-    helpers_module.triangulate_points = lambda ip, cp: triangulate_points(ip, cp, s)
-    helpers_module.calculate_reprojection_error = lambda ip, op, cp: calculate_reprojection_error(ip, op, cp, s)
-    helpers_module.calculate_reprojection_errors = lambda ip, op, cp: calculate_reprojection_errors(ip, op, cp, s)
-    helpers_module.find_point_correspondance_and_object_points = \
-        lambda ip, cp, fr: find_point_correspondance_and_object_points(ip, cp, fr, s)
-    helpers_module.bundle_adjustment = lambda ip, cp, sio: bundle_adjustment(ip, cp, sio, s)
-    helpers_module.locate_objects = lambda op, er: locate_objects(op, er, s)
+    repl = {
+        "triangulate_point": lambda ip, cp: triangulate_point(ip, cp, s),
+        "triangulate_points": lambda ip, cp: triangulate_points(ip, cp, s),
+        "calculate_reprojection_error": lambda ip, op, cp: calculate_reprojection_error(ip, op, cp, s),
+        "calculate_reprojection_errors": lambda ip, op, cp: calculate_reprojection_errors(ip, op, cp, s),
+        "find_point_correspondance_and_object_points":
+            lambda ip, cp, fr: find_point_correspondance_and_object_points(ip, cp, fr, s),
+        "bundle_adjustment": lambda ip, cp, sio: bundle_adjustment(ip, cp, sio, s),
+        "locate_objects": lambda op, er: locate_objects(op, er, s),
+    }
+    for name, fn in repl.items():
+        fn.__name__ = name
+        fn.__mocap_b200__ = True
+        setattr(helpers_module, name, fn)
+        for mod in also:
+            if hasattr(mod, name):
+                setattr(mod, name, fn)
     return s

@@ -175,3 +175,7 @@ if __name__ == "__main__":
         triangulate_case("tri_c16", 16, 200, seed=7)
     if "ba" in which:
         ba_case("ba_c4", 4, 40, seed=11)
+    if "ba8" in which:      # config-3 batch shape (about half an hour of reference CPU time)
+        ba_case("ba_c8", 8, 60, seed=12)
+    if "ba16" in which:     # reduced config-5 shape (16 cameras)
+        ba_case("ba_c16", 16, 96, seed=13)

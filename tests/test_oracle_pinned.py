@@ -183,3 +183,51 @@ def test_install_into_rebinds_the_live_reference_module():
         for n in names:
             setattr(helpers, n, saved[n])
         type(cams)._find_dot = saved_fd
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree only exists in the build container")
+def test_install_into_reaches_the_names_index_imported_by_value(monkeypatch, synth):
+    """index.py binds bundle_adjustment / triangulate_points / calculate_reprojection_errors BY VALUE
+    (``from helpers import ...``, index.py:1), so patching ``helpers`` alone leaves the calculate-camera-pose
+    handler (index.py:254,272,274,275 -- BASELINE config 5's caller) on the CPU functions.
+    ``install_into(helpers, index)`` must re-bind them there too: the unmodified handler is run and every one of
+    the three calls has to arrive in the replacement layer (which, in this GPU-less tier, is pointed back at the
+    reference's own functions so that the handler runs to its end)."""
+    import importlib
+    pkg = importlib.import_module("low-cost-mocap_b200")
+    api = importlib.import_module("low-cost-mocap_b200.api")
+    index, helpers, cams = ref_harness.load_reference_index(4)
+    names = list(api.PATCHED_NAMES)
+    saved_h = {n: getattr(helpers, n) for n in names}
+    saved_i = {n: getattr(index, n) for n in names if hasattr(index, n)}
+    assert set(saved_i) == {"bundle_adjustment", "triangulate_points", "calculate_reprojection_errors"}
+    saved_fd = type(cams)._find_dot
+    reached = []
+
+    def spy(name):
+        def f(*a):
+            reached.append(name)
+            return saved_h[name](*a[:-1])              # drop the session argument, run the reference's own code
+        return f
+
+    for n in names:                                    # every replacement, so that nested calls stay on the CPU here
+        monkeypatch.setattr(api, n, spy(n))
+    try:
+        pkg.install_into(helpers, index)
+        for n in saved_i:
+            assert getattr(index, n) is getattr(helpers, n) and getattr(index, n) is not saved_i[n]
+            assert getattr(index, n).__mocap_b200__
+        obs, poses, K, pts = synth.make_tracks(4, 30, seed=2, missing_frac=0.0)
+        import cv2
+        cv2.setRNGSeed(1)
+        index.socketio.events.clear()
+        index.calculate_camera_pose({"cameraPoints": obs.tolist()})
+        assert "bundle_adjustment" in reached and "calculate_reprojection_errors" in reached
+        assert reached.count("triangulate_points") >= 3 * 4 + 1       # 4 cheirality candidates per pair + the final call
+        assert index.socketio.events and index.socketio.events[-1][0][0] == "camera-pose"
+    finally:
+        for n, f in saved_h.items():
+            setattr(helpers, n, f)
+        for n, f in saved_i.items():
+            setattr(index, n, f)
+        type(cams)._find_dot = saved_fd
