@@ -130,6 +130,14 @@ MOCAP_API int mocap_match_triangulate_dev(mocap_ctx* ctx, const int32_t* blob_xy
 MOCAP_API int mocap_pipeline_dev(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets, int channels,
                        int threshold, double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
 
+/* mocap_pipeline_dev that also leaves, for every emitted point, the pixel of the winning correspondence in each
+ * camera: track_xy int32 [n_frame_sets][max_roots][n_cam][2], (-1, -1) where the camera has no view (NULL: not
+ * written).  This is the (F, C, 2) image_points array with None entries that bundle_adjustment receives
+ * (helpers.py:244, index.py:272), per triangulated point. */
+MOCAP_API int mocap_pipeline_tracks_dev(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets, int channels,
+                              int threshold, double* obj, double* err, int32_t* n_obj, int32_t* set_flags,
+                              int32_t* track_xy);
+
 /* Same with HOST buffers: frames are copied to the device in chunks overlapped with
  * compute, results copied back; returns after the results are in the host buffers.
  * For best speed pass page-locked memory (mocap_host_alloc). */
@@ -217,6 +225,9 @@ typedef struct mocap_ba_options {
                               reprojection error, then polish on the reference objective; 0: reference
                               iteration only */
     int    prefit_max_iter;  /* 50 */
+    int    engine;      /* 0 (default): the whole solve in ONE persistent, grid-synchronous kernel (k_ba_solve): no host round
+                              trips; 1: host-stepped (optimiser control on the host, one launch per phase, a stream
+                              synchronisation per step) -- the same algorithm, kept as a cross-check */
 } mocap_ba_options;
 
 typedef struct mocap_ba_report {
@@ -231,12 +242,34 @@ typedef struct mocap_ba_report {
     double prefit_cost_final;
     int    prefit_iterations;
     int    n_launches;     /* kernels launched by this call                            */
+    float  phase_ms[8];    /* device-resident solve only: wall time per phase, CTA 0's clock --
+                              0 set-up and control, 1 prefit: reduced camera system (Schur complement), 2 prefit: dense solve,
+                              3 prefit: back-substitution + trial cost, 4 polish: finite-difference Jacobian + normal equations,
+                              5 polish: tridiagonalisation, 6 polish: trust-region sub-problems, 7 polish: trial evaluations */
 } mocap_ba_report;
 
 MOCAP_API void mocap_ba_default_options(mocap_ba_options* opt);
 MOCAP_API int  mocap_bundle_adjust_host(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points,
                               double* R, double* t, const mocap_ba_options* opt,
                               mocap_ba_report* report);
+/* The same with DEVICE buffers, stream-ordered, never synchronises: ONE cooperative launch of k_ba_solve runs the
+ * whole bundle adjustment (residuals, Jacobians, Schur complement, the <= 90 x 90 dense solves, step control).
+ * obs double [n_points_max][n_cam][2], mask uint8 [n_points_max][n_cam]; n_points (device int32, may be NULL =
+ * n_points_max) is read by the kernel, so the count can come from mocap_tracks_to_observations_dev without a
+ * host round trip; R [n_cam][9], t [n_cam][3] device doubles in/out; opt is a HOST pointer (NULL = defaults; the
+ * engine field is ignored); report is a DEVICE pointer (may be NULL; status -3: no point with two views). */
+MOCAP_API int  mocap_bundle_adjust_dev(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points_max,
+                             const int32_t* n_points, double* R, double* t, const mocap_ba_options* opt,
+                             mocap_ba_report* report);
+/* Matcher output of a batch -> the explicit correspondences S4 consumes (BASELINE config 3: S1-S3, then one
+ * bundle adjustment per batch), on the device: track_xy int32 [n_frame_sets][max_roots][n_cam][2] as written by
+ * mocap_pipeline_tracks_dev ((-1, -1) = no view), n_obj / err the matcher's outputs; tracks whose reprojection
+ * error exceeds max_err are left out (max_err <= 0: keep all; err may then be NULL).  One row per kept track, in
+ * frame order then root order: obs double [capacity][n_cam][2], mask uint8 [capacity][n_cam]; *n_points (device)
+ * = number of rows written (<= capacity).  DEVICE pointers, stream-ordered. */
+MOCAP_API int  mocap_tracks_to_observations_dev(mocap_ctx* ctx, const int32_t* track_xy, const int32_t* n_obj,
+                                      const double* err, int n_frame_sets, double max_err, double* obs,
+                                      uint8_t* mask, int32_t* n_points, int capacity);
 /* residual vector of S4 at explicit poses (helpers.py:264-276); r float [n_points],
  * valid uint8 [n_points]; returns the number of valid residuals in *n_valid. HOST pointers. */
 MOCAP_API int  mocap_ba_residuals_host(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points,

@@ -26,14 +26,14 @@ class Config(C.Structure):
 
 class BAOptions(C.Structure):
     _fields_ = [("ftol", C.c_double), ("xtol", C.c_double), ("gtol", C.c_double),
-                ("max_nfev", C.c_int), ("jacobian", C.c_int), ("prefit", C.c_int), ("prefit_max_iter", C.c_int)]
+                ("max_nfev", C.c_int), ("jacobian", C.c_int), ("prefit", C.c_int), ("prefit_max_iter", C.c_int), ("engine", C.c_int)]
 
 
 class BAReport(C.Structure):
     _fields_ = [("cost_initial", C.c_double), ("cost_final", C.c_double), ("optimality", C.c_double),
                 ("n_iterations", C.c_int), ("n_fev", C.c_int), ("status", C.c_int), ("n_residuals", C.c_int),
                 ("prefit_cost_initial", C.c_double), ("prefit_cost_final", C.c_double),
-                ("prefit_iterations", C.c_int), ("n_launches", C.c_int)]
+                ("prefit_iterations", C.c_int), ("n_launches", C.c_int), ("phase_ms", C.c_float * 8)]
 
 
 # every symbol include/mocap_b200.h declares: name -> (restype, argtypes)
@@ -62,6 +62,9 @@ SYMBOLS = {
     "mocap_calibrate_init_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
     "mocap_ba_default_options": (None, [C.POINTER(BAOptions)]),
     "mocap_bundle_adjust_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.POINTER(BAOptions), C.POINTER(BAReport)]),
+    "mocap_bundle_adjust_dev": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, C.POINTER(BAOptions), _P]),
+    "mocap_tracks_to_observations_dev": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_double, _P, _P, _P, C.c_int]),
+    "mocap_pipeline_tracks_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "mocap_ba_residuals_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_int)]),
     "mocap_host_alloc": (C.c_int, [C.POINTER(_P), C.c_uint64]),
     "mocap_host_free": (None, [_P]),

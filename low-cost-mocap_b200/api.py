@@ -56,6 +56,12 @@ def _np_ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else C.c_void_p(0)
 
 
+def _report_dict(rep):
+    d = {f: getattr(rep, f) for f, _ in BAReport._fields_}
+    d["phase_ms"] = [float(v) for v in rep.phase_ms]
+    return d
+
+
 class MocapContext:
     """One libmocap_b200 context (one CUDA device, one stream, one camera rig)."""
 
@@ -231,16 +237,57 @@ class MocapContext:
                 "n": torch.empty((n_sets,), dtype=torch.int32, device=dev),
                 "flags": torch.empty((n_sets,), dtype=torch.int32, device=dev)}
 
-    def pipeline(self, frames, threshold=THRESHOLD, out=None):
-        """S1+S2+S3 on a device tensor of frame-sets [B, C, H, W] (or [B, C, H, W, 3])."""
+    def pipeline(self, frames, threshold=THRESHOLD, out=None, want_tracks=False):
+        """S1+S2+S3 on a device tensor of frame-sets [B, C, H, W] (or [B, C, H, W, 3]).  want_tracks (or an ``out``
+        that holds "track_xy"): also the winners' pixels per camera, int32 [B, max_roots, C, 2], (-1, -1) = no view."""
+        torch = _torch()
         ch = 3 if (frames.shape[-1] == 3 and frames.shape[-2] == self.width) else 1
         B = frames.numel() // (self.n_cam * self.width * self.height * ch)
         if out is None:
             out = self.alloc_tracks(B, frames.device)
+        if want_tracks and "track_xy" not in out:
+            out["track_xy"] = torch.empty((B, self.cfg.max_roots, self.n_cam, 2), dtype=torch.int32, device=frames.device)
         self.use_current_stream()
-        self._check(self.lib.mocap_pipeline_dev(self.h, _ptr(frames), B, ch, int(threshold),
-                                                _ptr(out["obj"]), _ptr(out["err"]), _ptr(out["n"]), _ptr(out["flags"])))
+        self._check(self.lib.mocap_pipeline_tracks_dev(self.h, _ptr(frames), B, ch, int(threshold), _ptr(out["obj"]), _ptr(out["err"]),
+                                                       _ptr(out["n"]), _ptr(out["flags"]), _ptr(out.get("track_xy"))))
         return out
+
+    def tracks_to_observations_dev(self, tracks, max_err=0.0, capacity=None, out=None):
+        """Matcher output of a batch (``pipeline(..., want_tracks=True)``) -> the explicit correspondences S4 consumes,
+        on the device, no synchronisation: dict obs f64 [capacity, C, 2], mask uint8 [capacity, C], n int32 [1]."""
+        torch = _torch()
+        B = tracks["n"].numel()
+        dev = tracks["n"].device
+        cap = int(capacity or B * self.cfg.max_roots)
+        if out is None:
+            out = {"obs": torch.empty((cap, self.n_cam, 2), dtype=torch.float64, device=dev),
+                   "mask": torch.empty((cap, self.n_cam), dtype=torch.uint8, device=dev),
+                   "n": torch.zeros((1,), dtype=torch.int32, device=dev)}
+        self.use_current_stream()
+        self._check(self.lib.mocap_tracks_to_observations_dev(self.h, _ptr(tracks["track_xy"]), _ptr(tracks["n"]), _ptr(tracks["err"]), B,
+                                                              float(max_err), _ptr(out["obs"]), _ptr(out["mask"]), _ptr(out["n"]), cap))
+        return out
+
+    def bundle_adjust_dev(self, obs, mask, R, t, n_points=None, report=None, ftol=1e-2, max_nfev=0, prefit=True, jacobian=1,
+                          prefit_max_iter=50):
+        """S4 wholly on the device (mocap_bundle_adjust_dev): obs f64 [P, C, 2], mask uint8 [P, C], R f64 [C, 3, 3] and
+        t f64 [C, 3] cuda tensors (R, t updated in place), n_points an int32 cuda tensor [1] or None.  One cooperative
+        launch, no synchronisation.  Returns the report as a uint8 cuda tensor (decode with ``decode_ba_report``)."""
+        torch = _torch()
+        opt = BAOptions()
+        self.lib.mocap_ba_default_options(C.byref(opt))
+        opt.ftol, opt.max_nfev, opt.prefit, opt.jacobian, opt.prefit_max_iter = ftol, max_nfev, 1 if prefit else 0, jacobian, prefit_max_iter
+        if report is None:
+            report = torch.zeros((C.sizeof(BAReport),), dtype=torch.uint8, device=obs.device)
+        self.use_current_stream()
+        self._check(self.lib.mocap_bundle_adjust_dev(self.h, _ptr(obs), _ptr(mask), obs.shape[0], _ptr(n_points), _ptr(R), _ptr(t),
+                                                     C.byref(opt), _ptr(report)))
+        return report
+
+    @staticmethod
+    def decode_ba_report(report):
+        rep = BAReport.from_buffer_copy(report.cpu().numpy().tobytes())
+        return _report_dict(rep)
 
     def pipeline_host(self, frames, threshold=THRESHOLD, out=None):
         """Same through HOST memory: frames is a (preferably pinned) uint8 cpu tensor / ndarray;
@@ -320,7 +367,7 @@ class MocapContext:
         self._check(self.lib.mocap_ba_residuals_host(self.h, _np_ptr(obs), _np_ptr(mask), F, _np_ptr(R), _np_ptr(t), _np_ptr(r), _np_ptr(valid), C.byref(nv)))
         return r[valid.astype(bool)]
 
-    def bundle_adjust(self, obs, mask, poses, ftol=1e-2, max_nfev=0):
+    def bundle_adjust(self, obs, mask, poses, ftol=1e-2, max_nfev=0, engine=0, prefit=True, jacobian=1):
         obs = np.ascontiguousarray(obs, dtype=np.float64)
         mask = np.ascontiguousarray(mask, dtype=np.uint8)
         R = np.ascontiguousarray(np.stack([np.asarray(p["R"], dtype=np.float64).reshape(3, 3) for p in poses]))
@@ -329,11 +376,11 @@ class MocapContext:
         self.lib.mocap_ba_default_options(C.byref(opt))
         opt.ftol = ftol
         opt.max_nfev = max_nfev
+        opt.engine, opt.prefit, opt.jacobian = engine, 1 if prefit else 0, jacobian
         rep = BAReport()
         self._check(self.lib.mocap_bundle_adjust_host(self.h, _np_ptr(obs), _np_ptr(mask), obs.shape[0], _np_ptr(R), _np_ptr(t), C.byref(opt), C.byref(rep)))
         out = [{"R": R[i].copy(), "t": t[i].copy()} for i in range(R.shape[0])]
-        report = {f: getattr(rep, f) for f, _ in BAReport._fields_}
-        return out, report
+        return out, _report_dict(rep)
 
     # -- accounting -----------------------------------------------------------------------
     def launch_count(self):

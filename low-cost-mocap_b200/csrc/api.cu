@@ -11,6 +11,7 @@ int blob_kernels_init(mocap_ctx* ctx);
 int match_kernels_init(mocap_ctx* ctx);
 int fused_kernel_init(mocap_ctx* ctx);
 int tma_kernel_init(mocap_ctx* ctx);
+int ba_dev_init(mocap_ctx* ctx);
 
 int mocap_fail(mocap_ctx* ctx, int code, const char* fmt, ...) {
     if (ctx) {
@@ -125,6 +126,7 @@ int mocap_create(mocap_ctx** out, const mocap_config* cfg) {
         }
         if ((st = fused_kernel_init(ctx)) != MOCAP_OK) break;
         if ((st = tma_kernel_init(ctx)) != MOCAP_OK) break;
+        if ((st = ba_dev_init(ctx)) != MOCAP_OK) break;
         if (ctx->tma_ctas_per_sm < 1) ctx->use_tma = 0;
     } while (0);
     if (st != MOCAP_OK) { mocap_destroy(ctx); return st; }
@@ -143,6 +145,7 @@ void mocap_destroy(mocap_ctx* ctx) {
     cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
     cudaFree(ctx->d_obj); cudaFree(ctx->d_err); cudaFree(ctx->d_nobj); cudaFree(ctx->d_setflags);
     cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_ba_ws);
     cudaFree(ctx->d_pp_m1); cudaFree(ctx->d_pp_m2); cudaFree(ctx->d_pp_rot);
     cudaFree(ctx->d_stat_acc);
     if (ctx->h_stat) cudaFreeHost(const_cast<unsigned long long*>(ctx->h_stat));
@@ -267,6 +270,11 @@ int mocap_match_triangulate_dev(mocap_ctx* ctx, const int32_t* blob_xy, const in
 // ---- S1+S2+S3 ------------------------------------------------------------------------------
 int mocap_pipeline_dev(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets, int channels, int threshold,
                        double* obj, double* err, int32_t* n_obj, int32_t* set_flags) {
+    return mocap_pipeline_tracks_dev(ctx, frames, n_frame_sets, channels, threshold, obj, err, n_obj, set_flags, nullptr);
+}
+
+int mocap_pipeline_tracks_dev(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets, int channels, int threshold,
+                              double* obj, double* err, int32_t* n_obj, int32_t* set_flags, int32_t* track_xy) {
     if (!ctx) return MOCAP_EINVAL;
     if (!frames || !obj || !err || !n_obj || n_frame_sets < 0 || (channels != 1 && channels != 3))
         return mocap_fail(ctx, MOCAP_EINVAL, "mocap_pipeline_dev: bad argument");
@@ -281,20 +289,23 @@ int mocap_pipeline_dev(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets, 
     if (st) return st;
     for (int s0 = 0; s0 < n_frame_sets; s0 += chunk) {
         const int ns = (n_frame_sets - s0 < chunk) ? n_frame_sets - s0 : chunk;
+        // the launchers hand this to the matcher (frame-set indices inside a launch group start at 0)
+        ctx->track_xy_cur = track_xy ? track_xy + (size_t)s0 * ctx->cfg.max_roots * C * 2 : nullptr;
         if (fused) {
             st = (ctx->use_tma ? launch_pipeline_tma : launch_pipeline_fused)(ctx, frames + (size_t)s0 * set_bytes, ns, threshold, obj + (size_t)s0 * ctx->cfg.max_roots * 3,
                                        err + (size_t)s0 * ctx->cfg.max_roots, n_obj + s0, set_flags ? set_flags + s0 : nullptr);
-            if (st) return st;
+            if (st) break;
             continue;
         }
         st = launch_detect(ctx, frames + (size_t)s0 * set_bytes, ns * C, channels, threshold,
                            ctx->d_blob_xy, ctx->d_blob_n, nullptr, ctx->d_img_flags);
-        if (st) return st;
+        if (st) break;
         st = launch_match(ctx, ctx->d_blob_xy, ctx->d_blob_n, ns, obj + (size_t)s0 * ctx->cfg.max_roots * 3,
                           err + (size_t)s0 * ctx->cfg.max_roots, n_obj + s0, set_flags ? set_flags + s0 : nullptr, nullptr);
-        if (st) return st;
+        if (st) break;
     }
-    return MOCAP_OK;
+    ctx->track_xy_cur = nullptr;
+    return st;
 }
 
 int mocap_pipeline_host(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets, int channels, int threshold,

@@ -640,7 +640,7 @@ extern "C" {
 
 void mocap_ba_default_options(mocap_ba_options* opt) {
     opt->ftol = 1e-2; opt->xtol = 1e-8; opt->gtol = 1e-8; opt->max_nfev = 0;
-    opt->jacobian = 1; opt->prefit = 1; opt->prefit_max_iter = 50;
+    opt->jacobian = 1; opt->prefit = 1; opt->prefit_max_iter = 50; opt->engine = 0;
 }
 
 int mocap_ba_residuals_host(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points,
@@ -682,6 +682,35 @@ int mocap_bundle_adjust_host(mocap_ctx* ctx, const double* obs, const uint8_t* m
     CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
     mocap_ba_options opt;
     if (opt_in) opt = *opt_in; else mocap_ba_default_options(&opt);
+    if (opt.engine == 0) {
+        // default: copy in, ONE launch of the device-resident solve (mocap_bundle_adjust_dev), copy out
+        const int C = ctx->cfg.n_cam;
+        auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t b_obs = al((size_t)n_points * C * 2 * 8), b_mask = al((size_t)n_points * C), b_R = al((size_t)C * 9 * 8), b_t = al((size_t)C * 3 * 8);
+        int st = ensure_scratch(ctx, b_obs + b_mask + b_R + b_t + al(sizeof(mocap_ba_report)));
+        if (st) return st;
+        unsigned char* p = static_cast<unsigned char*>(ctx->d_scratch);
+        double* d_obs = (double*)p; p += b_obs; uint8_t* d_mask = p; p += b_mask;
+        double* d_R = (double*)p; p += b_R; double* d_t = (double*)p; p += b_t;
+        mocap_ba_report* d_rep = (mocap_ba_report*)p;
+        cudaStream_t s = ctx->stream;
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_obs, obs, (size_t)n_points * C * 2 * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_mask, mask, (size_t)n_points * C, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_R, R, (size_t)C * 9 * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_t, t, (size_t)C * 3 * 8, cudaMemcpyHostToDevice, s));
+        st = mocap_bundle_adjust_dev(ctx, d_obs, d_mask, n_points, nullptr, d_R, d_t, &opt, d_rep);
+        if (st) return st;
+        mocap_ba_report rep;
+        CUDA_TRY(ctx, cudaMemcpyAsync(R, d_R, (size_t)C * 9 * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(t, d_t, (size_t)C * 3 * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(&rep, d_rep, sizeof(rep), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        if (rep.status == -3) return mocap_fail(ctx, MOCAP_EINVAL, "no point is seen by two cameras");
+        if (report) *report = rep;
+        return MOCAP_OK;
+    }
+    // engine 1: the host-stepped solve (optimiser control in trf_core.h, one launch per phase): kept as the
+    // cross-check of the device-resident solve
     mocap_ba_report rep;
     memset(&rep, 0, sizeof(rep));
     const uint64_t launches0 = ctx->launches;

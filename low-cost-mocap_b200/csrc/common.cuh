@@ -65,6 +65,9 @@ struct mocap_ctx {
     int       cap_sets;
     // generic scratch for the *_host triangulation / BA entry points
     void*     d_scratch; size_t scratch_bytes;
+    // S4 on the device (ba_dev.cu): workspace of k_ba_solve, launch shape
+    void*     d_ba_ws; size_t ba_ws_bytes; int ba_threads; int ba_grid; size_t ba_smem;
+    int32_t*  track_xy_cur;   // set for the duration of mocap_pipeline_tracks_dev: where the matcher leaves the winners' pixels
     // capture-side preprocessing
     int16_t*  d_pp_m1; uint16_t* d_pp_m2; int* d_pp_rot; int pp_in_w, pp_in_h;
     // accounting

@@ -23,6 +23,7 @@ struct FusedParams {
     const CameraTables* tb;
     int MB, RMAX, KC; uint32_t GMAX;
     double* obj; double* err; int32_t* n_obj; int32_t* set_flags;
+    int32_t* track_xy;             // optional: pixel of every winner per camera (mocap_pipeline_tracks_dev)
     size_t slab_bytes;
 };
 
@@ -79,7 +80,7 @@ __device__ __forceinline__ void finish_image(const FusedParams& P, unsigned char
     }
     WarpState ws = carve_warp_state(slab, P.RMAX, P.C, P.KC);
     match_triangulate_warp(P.tb, ws, P.blob_xy + (size_t)set * P.C * P.MB * 2, P.blob_n + (size_t)set * P.C, set, lane,
-                           P.C, P.MB, P.RMAX, P.KC, P.GMAX, P.obj, P.err, P.n_obj, P.set_flags, nullptr);
+                           P.C, P.MB, P.RMAX, P.KC, P.GMAX, P.obj, P.err, P.n_obj, P.set_flags, nullptr, P.track_xy);
     __syncwarp();
 }
 

@@ -183,7 +183,7 @@ k_pipeline_phased(const FusedParams P) {
                 const int set = (int)q.set[k];
                 WarpState ws = carve_warp_state(slab, P.RMAX, P.C, P.KC);
                 match_triangulate_warp(P.tb, ws, P.blob_xy + (size_t)set * P.C * P.MB * 2, P.blob_n + (size_t)set * P.C, set, lane,
-                                       P.C, P.MB, P.RMAX, P.KC, P.GMAX, P.obj, P.err, P.n_obj, P.set_flags, nullptr);
+                                       P.C, P.MB, P.RMAX, P.KC, P.GMAX, P.obj, P.err, P.n_obj, P.set_flags, nullptr, P.track_xy);
                 __syncwarp();
             }
         }

@@ -110,7 +110,8 @@ static __device__ __noinline__ void eval_group(const CameraTables* __restrict__ 
 static __device__ __noinline__ void match_triangulate_warp(
     const CameraTables* __restrict__ tb, WarpState ws, const int32_t* xy, const int32_t* nb, int set, int lane,
     int C, int MB, int RMAX, int KC, uint32_t GMAX, double* __restrict__ obj, double* __restrict__ err_out,
-    int32_t* __restrict__ n_obj, int32_t* __restrict__ set_flags, int32_t* __restrict__ chosen) {
+    int32_t* __restrict__ n_obj, int32_t* __restrict__ set_flags, int32_t* __restrict__ chosen,
+    int32_t* __restrict__ track_xy = nullptr) {
     int flags = 0;
 
     // roots from camera 0 (helpers.py:349,357)
@@ -253,6 +254,7 @@ static __device__ __noinline__ void match_triangulate_warp(
     double* obj_s = obj + (size_t)set * RMAX * 3;
     double* err_s = err_out + (size_t)set * RMAX;
     int32_t* ch_s = chosen ? chosen + (size_t)set * RMAX * C : nullptr;
+    int32_t* tx_s = track_xy ? track_xy + (size_t)set * RMAX * C * 2 : nullptr;   // the winner's pixel per camera, (-1, -1) = no view
     for (int r0 = 0; r0 < nr; r0 += 32) {
         const int r = r0 + lane;
         const bool has = r < nr && ws.gcount[r] > 0;
@@ -261,11 +263,20 @@ static __device__ __noinline__ void match_triangulate_warp(
             const int o = n_out + __popc(bal & ((1u << lane) - 1u));
             double X[3] = {ws.best_xe[4 * r], ws.best_xe[4 * r + 1], ws.best_xe[4 * r + 2]};
             const double e = ws.best_xe[4 * r + 3];
-            if (ch_s) {
+            if (ch_s || tx_s) {
                 int cams[MOCAP_MAX_CAM], pts[MOCAP_MAX_CAM];
                 const int nv = decode_group(ws, C, KC, r, ws.best_g[r], cams, pts);
-                for (int i = 0; i < C; ++i) ch_s[(size_t)o * C + i] = -1;
-                for (int k = 0; k < nv; ++k) ch_s[(size_t)o * C + cams[k]] = pts[k];
+                if (ch_s) {
+                    for (int i = 0; i < C; ++i) ch_s[(size_t)o * C + i] = -1;
+                    for (int k = 0; k < nv; ++k) ch_s[(size_t)o * C + cams[k]] = pts[k];
+                }
+                if (tx_s) {
+                    for (int i = 0; i < 2 * C; ++i) tx_s[(size_t)o * C * 2 + i] = -1;
+                    for (int k = 0; k < nv; ++k) {
+                        tx_s[((size_t)o * C + cams[k]) * 2 + 0] = __ldcg(xy + ((size_t)cams[k] * MB + pts[k]) * 2 + 0);
+                        tx_s[((size_t)o * C + cams[k]) * 2 + 1] = __ldcg(xy + ((size_t)cams[k] * MB + pts[k]) * 2 + 1);
+                    }
+                }
             }
             if (tb->use_world) {                               // helpers.py:96-103
                 const double* M = tb->world;

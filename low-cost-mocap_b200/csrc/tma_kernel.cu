@@ -214,6 +214,7 @@ int launch_pipeline_tma(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int t
     P.tb = ctx->d_tables;
     P.MB = c.max_blobs; P.RMAX = c.max_roots; P.KC = c.max_cands; P.GMAX = (uint32_t)c.max_groups;
     P.obj = obj; P.err = err; P.n_obj = n_obj; P.set_flags = set_flags;
+    P.track_xy = ctx->track_xy_cur;
     P.slab_bytes = fused_slab_bytes(c);
     const size_t smem = tma_smem_bytes(c);
     const long long mx = c.width > c.height ? c.width : c.height;

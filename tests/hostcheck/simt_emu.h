@@ -38,6 +38,11 @@ inline thread_local Tid tid{0, 0, 0};
 inline const char* volatile last_op[4096];
 inline const char* volatile last_where[4096];
 inline thread_local Block* blk = nullptr;
+// grids of several CTAs (persistent kernels with a grid-wide barrier, csrc/ba_device.cuh)
+inline thread_local Tid bid{0, 0, 0};
+inline Tid gdim{1, 1, 1};
+inline Tid bdim{1, 1, 1};
+inline std::barrier<>* grid_barrier = nullptr;
 
 inline void warp_sync(const char* what = "warp_sync") { last_op[tid.x] = what; blk->warp[tid.x >> 5]->arrive_and_wait(); last_op[tid.x] = "running"; }
 inline unsigned long long exchange(unsigned long long v, int src_lane) {      // value of lane src_lane of my warp
@@ -66,7 +71,30 @@ inline void launch(int nt, const std::function<void()>& fn) {
     if (watchdog.joinable()) watchdog.join();
 }
 
+// run fn on nb CTAs of nt threads each (blockIdx.x = 0 .. nb-1), all co-resident; simt_grid_sync() is a rendezvous
+// of every thread of the grid
+inline void launch_grid(int nb, int nt, const std::function<void()>& fn) {
+    std::vector<std::unique_ptr<Block>> blocks;
+    for (int b = 0; b < nb; ++b) blocks.emplace_back(new Block(nt));
+    std::barrier<> gb(nb * nt);
+    grid_barrier = &gb;
+    gdim = Tid{(unsigned)nb, 1, 1};
+    bdim = Tid{(unsigned)nt, 1, 1};
+    std::vector<std::thread> th;
+    for (int b = 0; b < nb; ++b)
+        for (int t = 0; t < nt; ++t)
+            th.emplace_back([&, b, t] { tid = Tid{(unsigned)t, 0, 0}; bid = Tid{(unsigned)b, 0, 0}; blk = blocks[b].get(); fn(); });
+    for (auto& t : th) t.join();
+    grid_barrier = nullptr;
+    gdim = Tid{1, 1, 1};
+}
+
 }  // namespace simt
+
+#define blockIdx (simt::bid)
+#define gridDim (simt::gdim)
+#define blockDim (simt::bdim)
+inline void simt_grid_sync() { simt::grid_barrier->arrive_and_wait(); }
 
 #ifndef __launch_bounds__
 #define __launch_bounds__(...)

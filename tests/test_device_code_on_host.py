@@ -457,3 +457,67 @@ def test_phased_kernel_on_host_equals_single_pass_kernel(fused_emu):
     for s in (0, 1, 3, 4, 5):
         k = d["n"][s]
         assert k == z["nroot"][s] and np.abs(d["obj"][s, :k] - z["obj"][s, :k]).max() <= X_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# S4: the persistent, grid-synchronous bundle adjustment kernel (csrc/ba_device.cuh) on the host
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ba_emu():
+    out = os.path.join(HC, "libba_dev_emu.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O2", "-shared", "-fPIC", "-pthread", "-I" + CUDA_INC, "-Wno-attributes",
+                           "-fno-strict-aliasing", "-o", out, os.path.join(HC, "ba_dev_emu_host.cpp")])
+    model = os.path.join(HC, "libba_host.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", model, os.path.join(HC, "ba_host.cpp"), "-lm"])
+    emu, host = ctypes.CDLL(out), ctypes.CDLL(model)
+    emu.hc_ba_solve_dev.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 3 + [ctypes.c_double] + [ctypes.c_int] * 6 + [ctypes.c_void_p]
+    host.hc_bundle_adjust.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 3 + [ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+
+    def solve(obs, mask, K, R, t, prefit, n_ctas, n_threads, jac_mode=1, max_nfev=0):
+        C = mask.shape[1]
+        obs = np.ascontiguousarray(obs, np.float64); mask = np.ascontiguousarray(mask, np.uint8)
+        Ks = np.ascontiguousarray(np.stack([K] * C)); R = np.ascontiguousarray(R.copy()); t = np.ascontiguousarray(t.copy())
+        rep = np.zeros(11)
+        assert emu.hc_ba_solve_dev(p(obs), p(mask), obs.shape[0], C, p(Ks), p(R), p(t), 1e-2, max_nfev, jac_mode, int(prefit), 50, n_ctas, n_threads, p(rep)) == 0
+        keys = ["cost_initial", "cost_final", "optimality", "n_iterations", "n_fev", "status", "n_residuals", "prefit_cost_initial",
+                "prefit_cost_final", "prefit_iterations", "smem"]
+        return R, t, dict(zip(keys, rep))
+
+    def model_solve(obs, mask, K, R, t, jac_mode=1):
+        C = mask.shape[1]
+        obs = np.ascontiguousarray(obs, np.float64); mask = np.ascontiguousarray(mask, np.uint8)
+        Ks = np.ascontiguousarray(np.stack([K] * C)); R = np.ascontiguousarray(R.copy()); t = np.ascontiguousarray(t.copy())
+        rep = np.zeros(7)
+        assert host.hc_bundle_adjust(p(obs), p(mask), obs.shape[0], C, p(Ks), p(R), p(t), 1e-2, 0, p(rep), jac_mode) == 0
+        return R, t, dict(zip(["cost_initial", "cost_final", "optimality", "n_iterations", "n_fev", "status", "n_jev"], rep))
+    return solve, model_solve
+
+
+def test_ba_kernel_on_host_equals_the_host_stepped_model(ba_emu):
+    """k_ba_solve without the prefit is scipy's trust-region iteration; its sub-problem runs on Cholesky factors of
+    A + alpha I where the host-stepped model (trf_core.h, itself checked against scipy) uses an eigen-decomposition.
+    Several CTAs of real threads: same iterations, evaluations, status, cost and poses."""
+    solve, model_solve = ba_emu
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ba_c4.npz"))
+    Rm, tm, rm = model_solve(z["obs"], z["mask"], z["K"], z["R_start"], z["t_start"])
+    for n_ctas, n_threads in ((1, 64), (3, 64)):
+        R, t, r = solve(z["obs"], z["mask"], z["K"], z["R_start"], z["t_start"], False, n_ctas, n_threads)
+        assert (r["n_iterations"], r["n_fev"], r["status"]) == (rm["n_iterations"], rm["n_fev"], rm["status"])
+        assert abs(r["cost_final"] - rm["cost_final"]) <= 1e-9 * rm["cost_final"] and abs(r["cost_initial"] - float(z["cost0"])) < 1e-6 * float(z["cost0"])
+        assert np.abs(R - Rm).max() < 1e-10 and np.abs(t - tm).max() < 1e-10
+        assert r["n_residuals"] == z["mask"].shape[0]
+
+
+def test_ba_kernel_on_host_with_prefit_beats_the_reference(ba_emu):
+    """The default path (Levenberg-Marquardt prefit with the tile-wise Schur complement, then the polish) ends below
+    the robust cost the real reference reaches from the same start (golden ba_c4), for any grid shape, and a
+    different grid shape changes only the rounding of the sums."""
+    solve, _ = ba_emu
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ba_c4.npz"))
+    R1, t1, r1 = solve(z["obs"], z["mask"], z["K"], z["R_start"], z["t_start"], True, 3, 64)
+    R2, t2, r2 = solve(z["obs"], z["mask"], z["K"], z["R_start"], z["t_start"], True, 2, 32)
+    assert r1["cost_final"] <= float(z["costf"]) and r1["prefit_cost_final"] < 1e-3 * r1["prefit_cost_initial"]
+    assert r1["status"] in (1, 2, 3, 4) and r1["smem"] < 227 * 1024
+    assert abs(r1["cost_final"] - r2["cost_final"]) < 1e-6 and np.abs(R1 - R2).max() < 1e-7 and np.abs(t1 - t2).max() < 1e-7
+    assert np.allclose(R1[0], np.eye(3)) and np.allclose(t1[0], 0)

@@ -2,6 +2,7 @@
 written by the real reference, against the oracle port on seeded inputs, and -- at BASELINE
 sizes -- through size-independent properties.  Run with ``-m gpu`` on a B200."""
 import importlib
+import os
 
 import numpy as np
 import pytest
@@ -1036,3 +1037,115 @@ def test_phased_pipeline_agrees_with_fused(torch, monkeypatch, name):
     for b in range(len(n)):
         assert np.array_equal(results["phased"]["obj"][b, :n[b]], results["fused"]["obj"][b, :n[b]])
         assert np.array_equal(results["phased"]["err"][b, :n[b]], results["fused"]["err"][b, :n[b]])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# S4 wholly on the device: k_ba_solve (one cooperative launch) behind mocap_bundle_adjust_dev / _host
+# ---------------------------------------------------------------------------------------------------------------
+def _tracks_case(C, F, seed):
+    obs_obj, poses, K, pts = synth.make_tracks(C, F, seed=seed, missing_frac=0.1)
+    start = synth.perturb_poses(poses, seed=seed + 1)
+    obs = np.array([[[-1 if v is None else v for v in cam] for cam in fr] for fr in obs_obj], dtype=np.float64)
+    mask = np.array([[cam[0] is not None for cam in fr] for fr in obs_obj], dtype=np.uint8)
+    return obs, mask, poses, start, K, pts
+
+
+@pytest.mark.parametrize("C,F,prefit", [(4, 40, True), (4, 40, False), (8, 1500, True), (16, 800, True), (2, 64, True), (3, 200, True)])
+def test_ba_device_engine_agrees_with_host_stepped(torch, C, F, prefit):
+    """The persistent grid-synchronous solve (engine 0) against the host-stepped solve (engine 1: optimiser control
+    of trf_core.h on the host, one launch per phase): same algorithm, so the same iteration counts, the same final
+    cost and the same poses up to the rounding of differently ordered sums."""
+    if C == 4:
+        z = load_golden("ba_c4")
+        obs, mask, K = z["obs"], z["mask"], z["K"]
+        start = [{"R": z["R_start"][c], "t": z["t_start"][c]} for c in range(C)]
+    else:
+        obs, mask, _, start, K, _ = _tracks_case(C, F, seed=100 + C)
+    ctx = _ctx(C)
+    ctx.set_cameras([K] * C, start)
+    out0, rep0 = ctx.bundle_adjust(obs, mask, start, engine=0, prefit=prefit)
+    out1, rep1 = ctx.bundle_adjust(obs, mask, start, engine=1, prefit=prefit)
+    assert rep0["n_launches"] == 1 and rep1["n_launches"] > 5
+    assert rep0["n_residuals"] == rep1["n_residuals"]
+    assert abs(rep0["cost_initial"] - rep1["cost_initial"]) <= 1e-9 * rep1["cost_initial"]
+    assert rep0["prefit_iterations"] == rep1["prefit_iterations"]
+    assert abs(rep0["prefit_cost_final"] - rep1["prefit_cost_final"]) <= 1e-6 * max(1.0, rep1["prefit_cost_final"])
+    assert (rep0["n_iterations"], rep0["n_fev"], rep0["status"]) == (rep1["n_iterations"], rep1["n_fev"], rep1["status"])
+    assert abs(rep0["cost_final"] - rep1["cost_final"]) <= 1e-6 * max(1.0, rep1["cost_final"])
+    for a, b in zip(out0, out1):
+        assert np.abs(a["R"] - b["R"]).max() < 1e-7 and np.abs(a["t"] - b["t"]).max() < 1e-7
+    assert np.allclose(out0[0]["R"], np.eye(3)) and np.allclose(out0[0]["t"], 0)
+
+
+def test_ba_device_engine_is_reproducible(torch):
+    """No atomics in the solve: two runs give the same bits."""
+    obs, mask, _, start, K, _ = _tracks_case(8, 3000, seed=5)
+    ctx = _ctx(8)
+    ctx.set_cameras([K] * 8, start)
+    a, ra = ctx.bundle_adjust(obs, mask, start)
+    b, rb = ctx.bundle_adjust(obs, mask, start)
+    ra.pop("phase_ms"); rb.pop("phase_ms")
+    assert ra == rb
+    for p, q in zip(a, b):
+        assert np.array_equal(p["R"], q["R"]) and np.array_equal(p["t"], q["t"])
+
+
+def test_pipeline_tracks_equal_chosen_correspondences(torch):
+    """mocap_pipeline_tracks_dev leaves the pixel of the winning correspondence per camera; it must be the blob the
+    `chosen` indices of the separate matcher name, and the device compaction must equal the torch one."""
+    z = load_golden("pipe_c8_m16")
+    C = 8
+    ctx = _ctx(C, max_roots=64)
+    ctx.set_cameras([z["K"]] * C, poses_from(z))
+    frames = torch.from_numpy(z["frames"]).cuda()
+    B = frames.shape[0]
+    for mode in ("fused", "split"):
+        os.environ["MOCAP_PIPELINE"] = mode
+        try:
+            c2 = _ctx(C, max_roots=64)
+        finally:
+            os.environ.pop("MOCAP_PIPELINE", None)
+        c2.set_cameras([z["K"]] * C, poses_from(z))
+        tr = c2.pipeline(frames, want_tracks=True)
+        d = c2.detect(frames.view(-1, 480, 640))
+        m = c2.match_triangulate(d["xy"], d["n"], want_chosen=True)
+        assert torch.equal(tr["n"], m["n"])
+        obs_ref, mask_ref = c2.tracks_to_observations(d["xy"], m["n"], m["chosen"])
+        o = c2.tracks_to_observations_dev(tr)
+        torch.cuda.synchronize()
+        n = int(o["n"].item())
+        assert n == obs_ref.shape[0] == int(m["n"].sum().item())
+        assert np.array_equal(o["mask"][:n].cpu().numpy(), mask_ref)
+        assert np.array_equal(o["obs"][:n].cpu().numpy(), obs_ref)
+        # error filter: keeps exactly the tracks at or below the bound, in order
+        bound = float(np.median(m["err"][0, :int(m["n"][0])].cpu().numpy()))
+        of = c2.tracks_to_observations_dev(tr, max_err=bound)
+        keep = np.concatenate([(m["err"][b, :int(m["n"][b])] <= bound).cpu().numpy() for b in range(B)])
+        nf = int(of["n"].item())
+        assert nf == int(keep.sum()) and np.array_equal(of["obs"][:nf].cpu().numpy(), obs_ref[keep])
+
+
+def test_config3_chain_on_the_device(torch):
+    """BASELINE config 3's step without the host: frames -> S1-S3 (+ winners' pixels) -> observations -> S4 from
+    perturbed poses, all enqueued on one stream with no synchronisation in between; the refined poses reproduce the
+    true rig up to the free global scale."""
+    C, M, B = 8, 16, 120
+    frames, truth, poses, K = synth.make_frame_pool(C, M, B, seed=21)
+    ctx = _ctx(C, max_roots=64)
+    ctx.set_cameras([K] * C, poses)
+    tr = ctx.pipeline(torch.from_numpy(frames).cuda(), want_tracks=True)
+    o = ctx.tracks_to_observations_dev(tr, max_err=2.0)
+    start = synth.perturb_poses(poses, seed=22)
+    R = torch.from_numpy(np.stack([p["R"] for p in start])).cuda().contiguous()
+    t = torch.from_numpy(np.stack([np.asarray(p["t"]).reshape(3) for p in start])).cuda().contiguous()
+    rep = ctx.bundle_adjust_dev(o["obs"], o["mask"], R, t, n_points=o["n"])
+    torch.cuda.synchronize()
+    rep = ctx.decode_ba_report(rep)
+    assert int((tr["flags"] != 0).sum().item()) == 0
+    assert rep["n_residuals"] == int(o["n"].item()) and rep["n_residuals"] >= B * M * 0.9
+    assert rep["status"] in (1, 2, 3, 4) and rep["cost_final"] < 1e-3 * rep["cost_initial"]
+    Rn, tn = R.cpu().numpy(), t.cpu().numpy()
+    s = np.linalg.norm(np.stack([p["t"] for p in poses])) / np.linalg.norm(tn)       # camera 0 pinned: only the scale is free
+    for c in range(C):
+        assert np.abs(Rn[c] - np.asarray(poses[c]["R"])).max() < 5e-3
+        assert np.abs(tn[c] * s - np.asarray(poses[c]["t"]).reshape(3)).max() < 2e-2
