@@ -43,7 +43,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_CAM, N_MARKERS, BATCH = 4, 4, 10000
-POOL = 250                       # distinct rendered frame-sets; the batch cycles through them
+POOL = 4096                      # distinct rendered frame-sets per GPU (>= 4096); the batch cycles through them
+CPU_POOL = 250                   # host-rendered frame-sets of the same generator for the CPU arm
+WITH_BA = False                  # config 3: one bundle adjustment per BA_BATCH frame-sets
+BA_BATCH = 1000
+BA_MAX_ERR = 2.0                 # tracks whose reprojection error exceeds this (px^2) are not handed to S4
 WIDTH, HEIGHT = 640, 480
 MAX_ROOTS = 16
 HBM_FALLBACK_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
@@ -99,7 +103,7 @@ class ClockSampler:
 
 def make_pool():
     synth = importlib.import_module("low-cost-mocap_b200.synth")
-    return synth.make_frame_pool(N_CAM, N_MARKERS, POOL, seed=0)
+    return synth.make_frame_pool(N_CAM, N_MARKERS, min(CPU_POOL, 250 if N_CAM <= 4 else 100), seed=0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -141,7 +145,26 @@ def cpu_pass(pool_obj, n_sets, n_workers):
 
 
 def host_cores():
-    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    """CPUs this process may actually use: the affinity mask, capped by the container's cgroup CPU quota (a GPU box
+    shows all 128 hardware threads in the mask but grants a fraction of them)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                       # cgroup v2: "<quota> <period>" or "max <period>"
+            q, p = f.read().split()[:2]
+            if q != "max":
+                quota = float(q) / float(p)
+    except Exception:
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:
+                q, p = float(f.read()), float(g.read())
+                if q > 0:
+                    quota = q / p
+        except Exception:
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(math.ceil(quota))))
+    return n
 
 
 class CpuArm:
@@ -181,25 +204,14 @@ class CpuArm:
         if eff < 0.5:
             print(f"bench.py: WARNING: CPU arm parallel efficiency {eff:.2f} < 0.5 ({value:.0f} frame-sets/s on {self.cores} "
                   f"cores vs {self.single_core:.0f} on one): the CPU figure understates the box", file=sys.stderr, flush=True)
+        aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         return {"value": value, "unit": "frame-sets/s", "cores": self.cores, "kind": "port", "sample": sample_text,
-                "single_core_value": self.single_core, "parallel_efficiency": eff}
+                "single_core_value": self.single_core, "parallel_efficiency": eff,
+                "cpus_in_affinity_mask": aff, "cores_note": "cores = min(affinity mask, cgroup CPU quota)"}
 
     def close(self):
         self.pool.close()
         self.pool.join()
-
-
-def oracle_tracks(frames, world, n_check=8):
-    """Part of the cpu_baseline leg: the oracle port's 3D points for the first frame-sets rank 0 owns (global
-    frame-sets 0, world, 2*world, ... of the round-robin stream), kept to check the GPU results against."""
-    port, poses = _W["port"], _W["poses"]
-    ref = []
-    for b in range(n_check):
-        fs = frames[(b * world) % len(frames)]
-        pts = [port.find_dot(np.repeat(img[:, :, None], 3, axis=2)) for img in fs]
-        e, o, _ = port.match_and_triangulate(pts, poses)
-        ref.append(np.asarray(o, dtype=np.float64).reshape(-1, 3))
-    return ref
 
 
 def compare_with_oracle(ref, out):
@@ -250,11 +262,76 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def render_pool_on_device(torch, dev, n_sets, seed, chunk=256):
+    """[n_sets, C, H, W] uint8 on the device: the synthetic stream of low-cost-mocap_b200/synth.py (same rig, same
+    marker random walk and separation rule -- those run on the host, they are cheap), rendered with torch: uniform
+    noise <= 40 under the threshold, every marker a Gaussian spot of peak 255.  Excluded from every timed region.
+    Also returns the true 3D points [n_sets, M, 3]."""
+    synth = importlib.import_module("low-cost-mocap_b200.synth")
+    st = synth.MarkerStream(N_CAM, N_MARKERS, seed=seed)
+    uv = np.empty((n_sets, N_CAM, N_MARKERS, 2))
+    truth = np.empty((n_sets, N_MARKERS, 3))
+    for b in range(n_sets):
+        pts, uvs, _ = st.next_frame_set(render=False)
+        uv[b], truth[b] = uvs, pts
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + seed)
+    frames = torch.empty((n_sets, N_CAM, HEIGHT, WIDTH), dtype=torch.uint8, device=dev)
+    sig = torch.from_numpy(st.sigmas).to(dev)                                     # [C, M]
+    r = 9
+    off = torch.arange(2 * r + 2, device=dev)
+    for b0 in range(0, n_sets, chunk):
+        b1 = min(n_sets, b0 + chunk)
+        fr = torch.randint(0, 41, (b1 - b0, N_CAM, HEIGHT, WIDTH), dtype=torch.uint8, device=dev, generator=g)
+        u = torch.from_numpy(uv[b0:b1, :, :, 0]).to(dev)                          # [b, C, M]
+        v = torch.from_numpy(uv[b0:b1, :, :, 1]).to(dev)
+        xs = (torch.floor(u).long() - r)[..., None, None] + off[None, None, None, None, :]     # [b, C, M, 1, P]
+        ys = (torch.floor(v).long() - r)[..., None, None] + off[None, None, None, :, None]     # [b, C, M, P, 1]
+        d2 = (xs.double() - u[..., None, None]) ** 2 + (ys.double() - v[..., None, None]) ** 2
+        val = torch.floor(255.0 * torch.exp(-d2 / (2.0 * sig[None, :, :, None, None] ** 2))).to(torch.uint8)
+        ok = (xs >= 0) & (xs < WIDTH) & (ys >= 0) & (ys < HEIGHT)
+        img = (torch.arange(b1 - b0, device=dev)[:, None] * N_CAM + torch.arange(N_CAM, device=dev)[None, :])[:, :, None, None, None]
+        idx = (img * HEIGHT + ys.clamp(0, HEIGHT - 1)) * WIDTH + xs.clamp(0, WIDTH - 1)
+        val = torch.where(ok, val, torch.zeros((), dtype=torch.uint8, device=dev))
+        fr.view(-1).scatter_reduce_(0, idx.reshape(-1), val.reshape(-1), "amax")
+        frames[b0:b1] = fr
+    return frames, truth, st.poses, st.K
+
+
+def csrc_hash():
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "low-cost-mocap_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(f.encode()); h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(workload, kernel_prefix):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
+    (profiles/traffic_<workload>.json, written by tools/ncu_traffic.py from the raw ncu CSV next to it); null when no
+    capture exists for the configuration or when the kernels have changed since it was taken."""
+    path = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+    except Exception:
+        return None, None
+    if not t.get("kernel", "").startswith(kernel_prefix):
+        return None, f"profiles/traffic_{workload}.json is for {t.get('kernel')}"
+    if t.get("csrc_sha") != csrc_hash():
+        return None, f"profiles/traffic_{workload}.json predates the current kernels (csrc {t.get('csrc_sha')} != {csrc_hash()})"
+    return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"]), f"profiles/traffic_{workload}.json <- {t.get('source')}"
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     pkg = importlib.import_module("low-cost-mocap_b200")
     sharding = importlib.import_module("low-cost-mocap_b200.sharding")
+    synth = pkg.synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -262,46 +339,108 @@ def run_gpu_arm(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch N > 1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
-    frames, truth, poses, K = make_pool()
+    with_ba = WITH_BA and world == 1 and not args.no_ba            # BASELINE config 3 (N = 1); config 4 (N > 1) has no S4
     cpu_res = None
     if rank == 0 and not args.profile:
-        # CPU baseline FIRST, before this process owns a CUDA context and 12 GB of pinned memory (forking
-        # worker processes out of such a process is slow and unsafe): the oracle port on this box's host
-        # cores, bounded sample of the same workload
+        # CPU baseline FIRST, before this process owns a CUDA context (forking worker processes out of such a
+        # process is slow and unsafe): the oracle port on this box's host cores, bounded sample of the same workload
+        # (frames from the same generator, rendered on the host)
+        frames, truth, poses, K = make_pool()
         arm = CpuArm(frames, K, poses)
         sample = arm.sample_for(12.0, BATCH)
         t_cpu = arm.run(sample)
         arm.close()
-        cpu_res = (arm, sample, t_cpu, oracle_tracks(frames, world))
+        s4_cpu = None
+        if with_ba:                                                 # one residual-vector evaluation of the reference's S4, bounded sample
+            obs, ps, Kt, _ = synth.make_tracks(N_CAM, 256, seed=3, missing_frac=0.1)
+            t0 = time.perf_counter()
+            _W["port"].ba_residuals(_W["port"].poses_to_params(ps), obs)
+            s4_cpu = (time.perf_counter() - t0) / 256
+        cpu_res = (arm, sample, t_cpu, s4_cpu)
+        del frames
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = pkg.MocapContext(N_CAM, WIDTH, HEIGHT, device=local, max_roots=MAX_ROOTS)
-    ctx.set_cameras([K] * N_CAM, poses)
 
-    # every rank owns BATCH frame-sets of the global stream of world*BATCH (round-robin ownership);
-    # content cycles through the rendered pool, offset per rank so shards differ
-    pool_dev = torch.from_numpy(frames).to(dev)
-    owned = torch.from_numpy(sharding.shard_indices(BATCH * world, rank, world)).to(dev)
-    batch = pool_dev[owned % POOL].contiguous()                   # [BATCH, C, H, W] uint8, 12.3 GB
+    # every rank owns BATCH frame-sets of the global stream of world*BATCH (round-robin ownership); each rank renders
+    # its own pool of POOL distinct frame-sets (seed = rank), the batch cycles through it
+    pool_dev, truth, poses, K = render_pool_on_device(torch, dev, POOL, seed=rank)
+    ctx.set_cameras([K] * N_CAM, poses)
+    if POOL == BATCH:
+        batch = pool_dev
+    else:
+        batch = pool_dev[torch.arange(BATCH, device=dev) % POOL].contiguous()      # [BATCH, C, H, W] uint8
+    first_sets = batch[:8].cpu().numpy()
     del pool_dev
+    torch.cuda.empty_cache()
     # the matcher writes straight into the all-gather send buffer (one flat allocation); two buffers in turn,
     # so that on the multi-GPU path batch k's tracks travel while batch k+1 is being processed
-    track_bufs = [sharding.TrackBuffer(BATCH, MAX_ROOTS, dev) for _ in range(2 if world > 1 else 1)]
-    pending = [None] * len(track_bufs)
-    out = track_bufs[0].views
+    n_bufs = 2 if (world > 1 or with_ba) else 1
+    track_bufs = [sharding.TrackBuffer(BATCH, MAX_ROOTS, dev) for _ in range(n_bufs)]
+    outs = [tb.views for tb in track_bufs]
+    pending = [None] * n_bufs
     bytes_per_step = batch.numel()
     step_no = [0]
 
-    def step():
-        k = step_no[0] % len(track_bufs)
+    # S4 per BA_BATCH frame-sets (config 3): observations and poses live on the device; the solve starts from the
+    # perturbed rig every time (rotvec sigma 0.03, t sigma 0.05) and runs on a side stream, so that it
+    # overlaps the next step's pass over HBM
+    if with_ba:
+        n_sub = BATCH // BA_BATCH
+        for o in outs:
+            o["track_xy"] = torch.empty((BATCH, MAX_ROOTS, N_CAM, 2), dtype=torch.int32, device=dev)
+        cap = BA_BATCH * MAX_ROOTS
+        ba_obs = [{"obs": torch.empty((cap, N_CAM, 2), dtype=torch.float64, device=dev),
+                   "mask": torch.empty((cap, N_CAM), dtype=torch.uint8, device=dev),
+                   "n": torch.zeros((1,), dtype=torch.int32, device=dev)} for _ in range(n_bufs * n_sub)]
+        start = synth.perturb_poses(poses, seed=10)
+        R0 = torch.from_numpy(np.stack([np.asarray(p["R"]) for p in start])).to(dev).contiguous()
+        t0_ = torch.from_numpy(np.stack([np.asarray(p["t"]).reshape(3) for p in start])).to(dev).contiguous()
+        ba_R = [R0.clone() for _ in range(n_bufs * n_sub)]
+        ba_t = [t0_.clone() for _ in range(n_bufs * n_sub)]
+        ba_rep = [None] * (n_bufs * n_sub)
+        side = torch.cuda.Stream(device=dev)
+        tracks_ready = [torch.cuda.Event() for _ in range(n_bufs)]
+        ba_done = [None] * n_bufs
+        ba_ms_events = []
+
+    def run_s4(k, timed):
+        """tracks of buffer k -> n_sub bundle adjustments, enqueued on the side stream"""
+        main = torch.cuda.current_stream(dev)
+        tracks_ready[k].record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(tracks_ready[k])
+            for j in range(n_sub):
+                i = k * n_sub + j
+                sl = slice(j * BA_BATCH, (j + 1) * BA_BATCH)
+                tr = {key: outs[k][key][sl] for key in ("track_xy", "n", "err")}
+                ctx.tracks_to_observations_dev(tr, max_err=BA_MAX_ERR, capacity=cap, out=ba_obs[i])
+                ba_R[i].copy_(R0); ba_t[i].copy_(t0_)
+                if timed:
+                    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ea.record(side)
+                ba_rep[i] = ctx.bundle_adjust_dev(ba_obs[i]["obs"], ba_obs[i]["mask"], ba_R[i], ba_t[i], n_points=ba_obs[i]["n"], report=ba_rep[i])
+                if timed:
+                    eb.record(side)
+                    ba_ms_events.append((ea, eb))
+            ev = torch.cuda.Event()
+            ev.record(side)
+            ba_done[k] = ev
+
+    def step(timed=False):
+        k = step_no[0] % n_bufs
         step_no[0] += 1
         if pending[k] is not None:
             pending[k].wait()                # this buffer's previous all-gather has read it
             pending[k] = None
-        ctx.pipeline(batch, out=track_bufs[k].views)
+        if with_ba and ba_done[k] is not None:
+            torch.cuda.current_stream(dev).wait_event(ba_done[k])    # the S4 that read this buffer has finished
+        ctx.pipeline(batch, out=outs[k])
+        if with_ba:
+            run_s4(k, timed)
         if world > 1:
             # ONE NCCL all-gather per batch, enqueued behind the pipeline kernel; consumers read views
             _, pending[k] = track_bufs[k].all_gather(async_op=True)
@@ -311,6 +450,10 @@ def run_gpu_arm(args):
             if w is not None:
                 w.wait()
                 pending[k] = None
+        if with_ba:
+            for ev in ba_done:
+                if ev is not None:
+                    torch.cuda.current_stream(dev).wait_event(ev)
 
     def sync_all():
         drain()
@@ -335,8 +478,8 @@ def run_gpu_arm(args):
     sync_all()
     e0.record()
     for _ in range(args.steps):
-        step()
-    drain()                                  # the stream now waits for the last all-gathers: they are inside the timed region
+        step(timed=True)
+    drain()                                  # the stream now waits for the last all-gathers / bundle adjustments: inside the timed region
     e1.record()
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -351,71 +494,164 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     value = BATCH * world * args.steps / (ms_total * 1e-3)
 
+    # ---- checks on every rank: no capacity overflow anywhere in the timed batch; the first frame-sets against the oracle
+    out = outs[(step_no[0] - 1) % n_bufs]
+    flags_set = int((out["flags"] != 0).sum().item())
+    problems = []
+    if flags_set:
+        problems.append(f"rank {rank}: {flags_set} frame-sets of the timed batch carry MOCAP_F_* overflow flags")
+    _cpu_init(K, poses)
+    port = _W["port"]
+    ref = []
+    for fs in first_sets:
+        pts = [port.find_dot(np.repeat(img[:, :, None], 3, axis=2)) for img in fs]
+        e, o, _ = port.match_and_triangulate(pts, poses)
+        ref.append(np.asarray(o, dtype=np.float64).reshape(-1, 3))
+    parity = compare_with_oracle(ref, out)
+    if not parity["point_counts_equal"] or parity["max_abs_3d_difference"] > 1e-7:
+        problems.append(f"rank {rank}: parity against the oracle failed: {parity}")
+    s4 = None
+    if with_ba:
+        reps = [ctx.decode_ba_report(r) for r in ba_rep]
+        Rn, tn = ba_R[-1].cpu().numpy(), ba_t[-1].cpu().numpy()
+        sc = np.linalg.norm(np.stack([np.asarray(p["t"]).reshape(3) for p in poses])) / np.linalg.norm(tn)
+        rot_err = max(float(np.abs(Rn[c] - np.asarray(poses[c]["R"])).max()) for c in range(N_CAM))
+        t_err = max(float(np.abs(tn[c] * sc - np.asarray(poses[c]["t"]).reshape(3)).max()) for c in range(N_CAM))
+        ba_ms = [a.elapsed_time(b) for a, b in ba_ms_events]
+        s4 = {"solves_per_step": n_sub, "frame_sets_per_solve": BA_BATCH, "points_per_solve": int(np.mean([r["n_residuals"] for r in reps])),
+              "max_err_px2": BA_MAX_ERR, "ms_per_solve": float(np.median(ba_ms)), "ms_per_solve_max": float(np.max(ba_ms)),
+              "launches_per_solve": 3, "status": sorted(set(r["status"] for r in reps)),
+              "cost_initial": float(np.mean([r["cost_initial"] for r in reps])), "cost_final": float(np.mean([r["cost_final"] for r in reps])),
+              "optimality": float(np.max([r["optimality"] for r in reps])),
+              "prefit_iterations": float(np.mean([r["prefit_iterations"] for r in reps])), "n_fev": float(np.mean([r["n_fev"] for r in reps])),
+              "phase_ms": [float(v) for v in np.mean([r["phase_ms"] for r in reps], axis=0)],
+              "pose_error_vs_true_rig": {"rotation_max_abs": rot_err, "translation_max_abs_after_scale": t_err},
+              "overlap": "side stream; the solves of step k run while step k+1 streams"}
+        if any(r["status"] not in (1, 2, 3, 4) for r in reps) or rot_err > 2e-2 or t_err > 5e-2:
+            problems.append(f"rank {rank}: S4 did not converge to the true rig: {s4}")
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, problems)
+        problems = [p for lst in gathered for p in lst]
+    if problems:
+        if rank == 0:
+            print("bench.py: RESULT CHECK FAILED\n  " + "\n  ".join(problems), file=sys.stderr, flush=True)
+        raise SystemExit(3)
+
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_only": True, "ms_per_step": ms_total / args.steps, "kernel_ms": kern_ms}), flush=True)
+            print(json.dumps({"profile_only": True, "ms_per_step": ms_total / args.steps, "kernel_ms": kern_ms, "s4": s4}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- e2e: host buffers through the C-ABI host entry point --------------------------------
+    # ---- e2e: host buffers ------------------------------------------------------------------------
     host_frames = torch.empty(batch.shape, dtype=torch.uint8).pin_memory()
     host_frames.copy_(batch)
     host_out = {"obj": torch.empty((BATCH, MAX_ROOTS, 3), dtype=torch.float64).pin_memory(),
                 "err": torch.empty((BATCH, MAX_ROOTS), dtype=torch.float64).pin_memory(),
                 "n": torch.empty((BATCH,), dtype=torch.int32).pin_memory(),
                 "flags": torch.empty((BATCH,), dtype=torch.int32).pin_memory()}
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
     e2e_steps = max(1, min(args.steps, 3))
-    ctx.pipeline_host(host_frames, out=host_out)                  # warm-up (allocates staging)
+    if not with_ba:
+        def e2e_step():                                              # the C-ABI host entry point: returns with results in host memory
+            ctx.pipeline_host(host_frames, out=host_out)
+        e2e_api = "mocap_pipeline_host (H2D in chunks overlapped with compute, D2H of the tracks)"
+    else:
+        # config 3 through host buffers: frames travel H2D in chunks (copy stream, two device buffers), every chunk
+        # goes through mocap_pipeline_tracks_dev, every BA_BATCH frame-sets through S4, tracks and poses travel D2H
+        chunk = BA_BATCH
+        stage = [torch.empty((chunk,) + tuple(batch.shape[1:]), dtype=torch.uint8, device=dev) for _ in range(2)]
+        copy_s = torch.cuda.Stream(device=dev)
+        host_R = torch.empty((BATCH // chunk, N_CAM, 3, 3), dtype=torch.float64).pin_memory()
+        host_t = torch.empty((BATCH // chunk, N_CAM, 3), dtype=torch.float64).pin_memory()
+        d2h += host_R.numel() * 8 + host_t.numel() * 8
+        dev_out = ctx.alloc_tracks(BATCH, dev)
+        dev_out["track_xy"] = outs[0]["track_xy"]
+
+        def e2e_step():
+            main = torch.cuda.current_stream(dev)
+            copied = [None, None]
+            used = [None, None]
+            for ci in range(BATCH // chunk):
+                bi = ci % 2
+                with torch.cuda.stream(copy_s):
+                    if used[bi] is not None:
+                        copy_s.wait_event(used[bi])
+                    stage[bi].copy_(host_frames[ci * chunk:(ci + 1) * chunk], non_blocking=True)
+                    ev = torch.cuda.Event(); ev.record(copy_s); copied[bi] = ev
+                main.wait_event(copied[bi])
+                sl = slice(ci * chunk, (ci + 1) * chunk)
+                tr = {key: dev_out[key][sl] for key in ("obj", "err", "n", "flags", "track_xy")}
+                ctx.pipeline(stage[bi], out=tr)
+                ev = torch.cuda.Event(); ev.record(main); used[bi] = ev
+                ctx.tracks_to_observations_dev(tr, max_err=BA_MAX_ERR, capacity=cap, out=ba_obs[0])
+                ba_R[0].copy_(R0); ba_t[0].copy_(t0_)
+                ctx.bundle_adjust_dev(ba_obs[0]["obs"], ba_obs[0]["mask"], ba_R[0], ba_t[0], n_points=ba_obs[0]["n"], report=ba_rep[0])
+                host_R[ci].copy_(ba_R[0], non_blocking=True); host_t[ci].copy_(ba_t[0], non_blocking=True)
+            for key in ("obj", "err", "n", "flags"):
+                host_out[key].copy_(dev_out[key], non_blocking=True)
+            torch.cuda.synchronize(dev)
+        e2e_api = ("MocapContext.pipeline(want_tracks) + tracks_to_observations_dev + bundle_adjust_dev per 1000 frame-sets, frames H2D in "
+                   "chunks from pinned memory on a copy stream, tracks and refined poses D2H")
+    e2e_step()                                                      # warm-up (allocates staging)
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.pipeline_host(host_frames, out=host_out)              # returns with results in host memory
+        e2e_step()
     torch.cuda.synchronize(dev)
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = BATCH * world * e2e_steps / float(dt.item())
-    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
     same = bool((host_out["n"].to(dev) == out["n"]).all().item())
 
-    kernel_name = ("k_threshold_segments_c1 (three-kernel pipeline)" if os.environ.get("MOCAP_PIPELINE") == "split"
+    split = os.environ.get("MOCAP_PIPELINE") == "split" or (os.environ.get("MOCAP_PIPELINE") is None and N_CAM * N_MARKERS > 48)
+    kernel_name = ("k_threshold_segments_c1 (stream kernel of the three-kernel pipeline)" if split
                    else "k_pipeline_fused (threshold + blob reduce + match/DLT in one pass)")
-    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this
-    # workload (profiles/ncu_full_r01_final.csv: dram__bytes_read.sum 12.311724 GB + dram__bytes_write.sum
-    # 30.966272 MB per launch of 10000 frame-sets); null for configurations that capture does not cover
-    traffic = 12311724000 + 30966272 if (os.environ.get("MOCAP_PIPELINE") != "split" and BATCH == 10000 and N_CAM == 4) else None
+    traffic, traffic_src = committed_traffic(args.workload, "k_threshold_segments" if split else "k_pipeline_fused")
     if rank == 0:
         peak, peak_src = measured_peak()
         # algorithmic bytes: C*W*H bytes per frame-set, read exactly once; per launch of the timed kernel:
-        # step bytes * steps / launches (one launch per step for the fused kernel, three for the split pipeline)
+        # step bytes * steps / launches
         alg_bytes = bytes_per_step * args.steps / kern_n if kern_n else None
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
-        arm, sample, t_cpu, ref_tracks = cpu_res
-        parity = compare_with_oracle(ref_tracks, out)
-        gpu_points = int(out["n"][:1].sum().item())
+        arm, sample, t_cpu, s4_cpu = cpu_res
+        stages = "S1 blob + S2 epipolar + S3 DLT" + (f" + S4 bundle adjustment per {BA_BATCH} frame-sets" if with_ba else "")
+        config_no = "2" if N_CAM == 4 else ("3" if with_ba else ("4" if world > 1 else "3 without S4"))
+        cpu_rep = arm.report(sample / t_cpu, f"{sample} frame-sets of the same workload (S1-S3), one worker process per core")
+        if with_ba:
+            n_par = 1 + 7 * (N_CAM - 1)
+            cpu_rep["s4_note"] = ("S1-S3 only: the reference's S4 on one 1000-frame batch cannot be timed in a bounded sample -- one residual-vector "
+                                  f"evaluation costs {s4_cpu * 1e3:.2f} ms per point on one core (measured on 256 points), i.e. "
+                                  f"{s4_cpu * s4['points_per_solve']:.1f} s per evaluation and {s4_cpu * s4['points_per_solve'] * (n_par + 1):.0f} s per "
+                                  f"finite-difference Jacobian ({n_par + 1} evaluations) of such a batch")
         line = {
-            "metric": f"mocap frame-sets/s ({N_CAM}-cam 640x480 synthetic, blob+epipolar+DLT)",
+            "metric": f"mocap frame-sets/s ({N_CAM}-cam 640x480 synthetic, {'blob+epipolar+DLT' + ('+bundle adjustment' if with_ba else '')})",
             "value": value, "unit": "frame-sets/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 pixels -> int64 moments -> f64 geometry", "data": "synthetic",
-            "config": {"workload": (f"BASELINE config {'2' if N_CAM == 4 else '3/4 shape'}: {N_CAM} cameras, {N_MARKERS} markers, {BATCH} frame-sets "
-                                    "of 640x480 uint8 per GPU per step, S1 blob + S2 epipolar + S3 DLT"),
+            "config": {"workload": (f"BASELINE config {config_no}: {N_CAM} cameras, {N_MARKERS} markers, {BATCH} frame-sets "
+                                    f"of 640x480 uint8 per GPU per step, {stages}"),
                        "cameras": N_CAM, "markers": N_MARKERS, "frame_sets_per_step_per_gpu": BATCH,
                        "distinct_frame_sets": POOL, "l2": f"inputs ({BATCH * N_CAM * 307200 / 1e9:.1f} GB per step) larger than L2, no flush needed",
                        "parallelism": f"frame-set round-robin over {world} GPU(s), one NCCL all-gather of tracks per batch" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "frame-sets/s", "h2d_bytes_per_step": int(bytes_per_step),
-                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "matches_resident_path": same},
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "matches_resident_path": same, "api": e2e_api,
+                    "bound": "PCIe: the frames cross the link once (55 GB/s measured); only more GPUs (one link each) move this figure"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes) if alg_bytes else None,
                          "avg_launch_ms": kern_ms, "launches_timed": kern_n,
                          "whole_step_frac": (bytes_per_step * args.steps / (ms_total * 1e-3) / 1e9) / peak},
-            "cpu_baseline": arm.report(sample / t_cpu, f"{sample} frame-sets of the same workload, one worker process per core"),
-            "parity_vs_oracle": parity,
+            "cpu_baseline": cpu_rep,
+            "parity_vs_oracle": parity, "overflow_flags_in_timed_batch": flags_set,
             "clocks": clocks,
         }
+        if s4:
+            line["s4"] = s4
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -429,14 +665,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4m4", choices=["c4m4", "c8m16"],
-                    help="c4m4 (default): BASELINE config 2, the configuration the metric is quoted on; c8m16: the shape of "
-                         "configs 3/4 (8 cameras, 16 markers, 4000 frame-sets per GPU per step) as a secondary figure")
+                    help="c4m4 (default): BASELINE config 2, the configuration the metric is quoted on; c8m16: 8 cameras, 16 markers, 4000 "
+                         "frame-sets per GPU per step -- at N = 1 BASELINE config 3 (S1-S3 plus one S4 per 1000 frame-sets), at N > 1 "
+                         "config 4 (S1-S3, round-robin shards, one NCCL all-gather of tracks per batch)")
+    ap.add_argument("--no-ba", action="store_true", help="c8m16 at N = 1 without S4 (the S1-S3 figure of the config-3 shape)")
     ap.add_argument("--profile", action="store_true",
                     help="resident steps only (no e2e, no CPU baseline): for runs under ncu; prints no bench line")
     args = ap.parse_args()
     if args.workload == "c8m16":
-        global N_CAM, N_MARKERS, BATCH, POOL, MAX_ROOTS
-        N_CAM, N_MARKERS, BATCH, POOL, MAX_ROOTS = 8, 16, 4000, 100, 64
+        global N_CAM, N_MARKERS, BATCH, POOL, MAX_ROOTS, WITH_BA
+        N_CAM, N_MARKERS, BATCH, POOL, MAX_ROOTS, WITH_BA = 8, 16, 4000, 4000, 64, True
     if args.impl == "reference":
         run_reference_arm(args)
     else:

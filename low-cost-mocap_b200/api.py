@@ -26,7 +26,7 @@ from ._lib import MocapError, Config, BAOptions, BAReport, check
 THRESHOLD = 51   # cv.threshold(grey, 255*0.2, 255, THRESH_BINARY) on uint8 == pix > 51 (helpers.py:146)
 
 # MOCAP_F_* bits of include/mocap_b200.h
-F_SEGMENTS, F_BLOBS, F_ROOTS, F_CANDS, F_GROUPS = 1, 2, 4, 8, 16
+F_SEGMENTS, F_BLOBS, F_ROOTS, F_CANDS, F_GROUPS, F_HOLES = 1, 2, 4, 8, 16, 32
 _FLAG_NAMES = {F_SEGMENTS: "max_segments", F_BLOBS: "max_blobs", F_ROOTS: "max_roots", F_CANDS: "max_cands",
                F_GROUPS: "max_groups"}
 # the reference is unbounded; the drop-in mirrors run with the compile-time maxima and raise on overflow
@@ -37,6 +37,9 @@ def raise_on_overflow(flags, what):
     """The reference keeps every contour / root / candidate group; a result truncated at a configured
     capacity would differ from it silently, so the mirrors turn any MOCAP_F_* bit into an error."""
     flags = int(flags)
+    if flags & F_HOLES:
+        raise MocapError(-1, f"{what}: a blob has a hole; cv.findContours(RETR_TREE) would give the hole a contour (one more "
+                             f"point) and fill the outer one -- not reproduced by this library (MOCAP_F_HOLES)")
     if flags:
         names = [n for b, n in _FLAG_NAMES.items() if flags & b]
         raise MocapError(-1, f"{what}: capacity overflow ({', '.join(names)}); results would be truncated "

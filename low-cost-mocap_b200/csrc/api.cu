@@ -300,8 +300,10 @@ int mocap_pipeline_tracks_dev(mocap_ctx* ctx, const uint8_t* frames, int n_frame
         st = launch_detect(ctx, frames + (size_t)s0 * set_bytes, ns * C, channels, threshold,
                            ctx->d_blob_xy, ctx->d_blob_n, nullptr, ctx->d_img_flags);
         if (st) break;
+        ctx->img_flags_cur = ctx->d_img_flags;
         st = launch_match(ctx, ctx->d_blob_xy, ctx->d_blob_n, ns, obj + (size_t)s0 * ctx->cfg.max_roots * 3,
                           err + (size_t)s0 * ctx->cfg.max_roots, n_obj + s0, set_flags ? set_flags + s0 : nullptr, nullptr);
+        ctx->img_flags_cur = nullptr;
         if (st) break;
     }
     ctx->track_xy_cur = nullptr;
@@ -357,8 +359,10 @@ int mocap_pipeline_host(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets,
         st = launch_detect(ctx, ctx->d_stage[k], ns * C, channels, threshold, ctx->d_blob_xy, ctx->d_blob_n, nullptr, ctx->d_img_flags);
         if (st) break;
         CUDA_TRY(ctx, cudaEventRecord(ctx->stage_free[k], ctx->stream));
+        ctx->img_flags_cur = ctx->d_img_flags;
         st = launch_match(ctx, ctx->d_blob_xy, ctx->d_blob_n, ns, ctx->d_obj + (size_t)s0 * RM * 3, ctx->d_err + (size_t)s0 * RM,
                           ctx->d_nobj + s0, ctx->d_setflags + s0, nullptr);
+        ctx->img_flags_cur = nullptr;
         if (st) break;
     }
     if (st) return st;

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "geom.cuh"
 #include "trf_core.h"
+#include "ba_device.cuh"          // BA_PREFIT_REL_STOP and the device-resident solve's declarations
 
 struct BAColumn { int cam; int pad; double Rt[12]; };     // pose of ONE camera replaced (cam < 0: none)
 
@@ -562,7 +563,7 @@ int prefit(DeviceBA& P, std::vector<double>& Rt, int max_iter, mocap_ba_report* 
             double* tmp = P.d_X; P.d_X = P.d_Xnew; P.d_Xnew = tmp;
             cost = cost_new;
             lambda = fmax(lambda * 0.3, 1e-12);
-            if (rel < 1e-10) { ++it; break; }
+            if (rel < BA_PREFIT_REL_STOP) { ++it; break; }
         } else {
             CUDA_TRY(ctx, upload(Rt));                       // back to the accepted poses
             CUDA_TRY(ctx, cudaStreamSynchronize(s));

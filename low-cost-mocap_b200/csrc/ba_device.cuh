@@ -27,6 +27,10 @@
 #include "common.cuh"
 #include "geom.cuh"
 
+// the prefit stops when an accepted step lowers the squared pixel error by less than this fraction (shared with the
+// host-stepped solve in ba.cu): the polish that follows works on a float32-quantised objective whose resolution is
+// coarser than that
+#define BA_PREFIT_REL_STOP 1e-7
 #define BA_TILE 32                 // points per tile (one warp = one column of a tile in the finite-difference pass)
 #define BA_MAX_N (6 * (MOCAP_MAX_CAM - 1))
 
@@ -441,8 +445,8 @@ BA_DEV void ba_grid_sum3(const BAParams& P, int slot, const double v[3], double 
     double* cp = P.cpart + (size_t)slot * G * 4;
     if (threadIdx.x == 0) { cp[4 * blockIdx.x] = v[0]; cp[4 * blockIdx.x + 1] = v[1]; cp[4 * blockIdx.x + 2] = v[2]; }
     ba_grid_sync(P.bar);
-    double a = 0.0, b = 0.0, c = 0.0;
-    for (int g = 0; g < G; ++g) { a += cp[4 * g]; b += cp[4 * g + 1]; c += cp[4 * g + 2]; }
+    double a = 0.0, b = 0.0, c = 0.0;                              // every thread the same sum, in CTA order
+    for (int g = 0; g < G; ++g) { a += __ldcg(cp + 4 * g); b += __ldcg(cp + 4 * g + 1); c += __ldcg(cp + 4 * g + 2); }
     tot[0] = a; tot[1] = b; tot[2] = c;
 }
 
@@ -451,12 +455,23 @@ BA_DEV void ba_reduce_system(const BAParams& P, const BAShared& S, int n_entries
     const int tid = threadIdx.x, nt = blockDim.x, G = gridDim.x, b = blockIdx.x;
     for (int e = tid; e < n_entries; e += nt) P.part[(size_t)b * P.pstride + e] = S.acc[e];
     ba_grid_sync(P.bar);
+    // every CTA adds its slice of the entries over all CTAs: 16 threads per entry fetch the partials side by side
+    // (the loads of one thread are independent), then one thread adds the 16 sub-sums in a fixed order
     const int per = (n_entries + G - 1) / G;
     const int e0 = b * per, e1 = (e0 + per < n_entries) ? e0 + per : n_entries;
-    for (int e = e0 + tid; e < e1; e += nt) {
+    for (int base = e0; base < e1; base += nt / 16) {
+        const int e = base + tid / 16, j = tid & 15;
         double s = 0.0;
-        for (int g = 0; g < G; ++g) s += P.part[(size_t)g * P.pstride + e];
-        P.fin[e] = s;
+        if (e < e1 && tid / 16 < nt / 16)
+            for (int g = j; g < G; g += 16) s += P.part[(size_t)g * P.pstride + e];
+        __syncthreads();
+        S.scratch[tid] = s;
+        __syncthreads();
+        if (j == 0 && e < e1 && tid / 16 < nt / 16) {
+            double t = 0.0;
+            for (int q = 0; q < 16; ++q) t += S.scratch[tid + q];
+            P.fin[e] = t;
+        }
     }
     ba_grid_sync(P.bar);
 }
@@ -1087,7 +1102,7 @@ BA_DEV void ba_solve_body(const BAParams& P, unsigned char* smem) {
                     const double rel = (cost - cost_new) / fmax(cost, 1e-300);
                     ctl->pf_cost1 = cost_new;
                     ctl->lambda = fmax(lambda * 0.3, 1e-12);
-                    if (rel < 1e-10) ctl->go = 0;
+                    if (rel < BA_PREFIT_REL_STOP) ctl->go = 0;
                 }
             } else if (tid == 0) {
                 ctl->pf_cost1 = cost;

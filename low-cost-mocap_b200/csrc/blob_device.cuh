@@ -319,6 +319,7 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
             const uint32_t e2 = sm.seg[i + 1];
             if ((e2 >> 16) == p + 1 && (e2 & 1u)) uf_unite(sm.parent, id, sm.base[i + 1]);
         }
+        unsigned U = 0;                                            // 18-bit window of row y-1 over columns 16*sc-1 .. 16*sc+16
         if (y > 0) {                                               // the <= 3 segments of row y-1 that touch this run
             const unsigned ext = (rb | (rb << 1) | (rb >> 1)) & 0xffffu;
             const uint32_t q = p - SPR;
@@ -327,6 +328,9 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
                 const uint32_t ej = sm.seg[j], pj = ej >> 16;
                 if (pj > q + 1) break;
                 const unsigned mm = ej & 0xffffu;
+                if (pj == q) U |= mm << 1;
+                else if (pj + 1 == q) U |= (mm >> 15) & 1u;
+                else if (sc + 1 < SPR) U |= (mm & 1u) << 17;
                 if (pj == q) {
                     unsigned sbits = mm, r = 0;
                     while (sbits) {
@@ -342,6 +346,13 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
                     if ((rb & 0x8000u) && (mm & 1u)) uf_unite(sm.parent, id, sm.base[j]);
                 }
             }
+        }
+        // Euler number, part 1 (see step 5): the run's first pixel opens a new run of (row y-1 | row y) that
+        // row y-1 does not own -- neither the pixel above it nor the one above-left is set (above-left-of-left is
+        // decided in step 5 together with this row's own left neighbour).  Kept in bit 15 of node_seg (< 4096).
+        {
+            const int s0 = __ffs((int)rb);                          // window index of the run's first pixel (bit + 1)
+            if (!((U >> s0) & 1u) && !((U >> (s0 - 1)) & 1u)) sm.node_seg[id] |= 0x8000u;
         }
     }
     gsync<NT>();
@@ -379,7 +390,8 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
     for (unsigned id = tid; id < n_runs; id += NT) {
         const unsigned blob = sm.rank[sm.parent[id]];
         if (blob >= (unsigned)ACC) continue;
-        const int i = sm.node_seg[id];
+        const int i = sm.node_seg[id] & 0x7fff;
+        const unsigned up_open = sm.node_seg[id] >> 15;
         const unsigned rb = sm.node_bits[id];
         const uint32_t e = sm.seg[i];
         const uint32_t p = e >> 16;
@@ -417,6 +429,16 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
         const long long a2 = 2ll * nf + ntl + ntr + nbl + nbr;
         const long long sx6 = 6 * sxf + 3ll * nf + 3 * (sx_tl + sx_tr + sx_bl + sx_br) + 2ll * (ntl + nbl) + (ntr + nbr);
         const long long sy6 = (6ll * y + 3) * nf + (3ll * y + 2) * (ntl + ntr) + (3ll * y + 1) * (nbl + nbr);
+        // Euler number of the blob (components - holes, 8-connectivity) from runs: sum over rows of the runs of
+        // (row y-1 | row y), minus the runs of every row (two rows whose runs touch merge into one run of the OR, and
+        // the touching graph between two rows is a forest).  Each run of an OR is counted at its first pixel, by the
+        // run that holds it; only a run that is not the continuation of a run of the left segment can start one.
+        int euler = 0;
+        {
+            const int s0 = __ffs((int)rb);                          // window index of the run's first pixel
+            if (!((T >> (s0 - 1)) & 1u))                            // a true run start: -1 for the row's own run count,
+                euler = (int)(!((Bw >> (s0 - 1)) & 1u)) + (int)(up_open && true) - 1;   // +1 per OR-run it opens (below / above)
+        }
         if (WIDE) {
             unsigned long long* a = sm.acc + 4 * blob;
             if (a2) {
@@ -424,7 +446,7 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
                 atomicAdd(a + 1, (unsigned long long)sx6);
                 atomicAdd(a + 2, (unsigned long long)sy6);
             }
-            atomicAdd(a + 3, (unsigned long long)__popc(rb));
+            atomicAdd(a + 3, (unsigned long long)__popc(rb) + ((unsigned long long)(long long)euler << 32));
         } else {                                                   // 6*max(W,H)*W*H < 2^32: native 32-bit shared atomics
             unsigned* a = reinterpret_cast<unsigned*>(sm.acc) + 4 * blob;
             if (a2) {
@@ -432,7 +454,7 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
                 atomicAdd(a + 1, (unsigned)sx6);
                 atomicAdd(a + 2, (unsigned)sy6);
             }
-            atomicAdd(a + 3, (unsigned)__popc(rb));
+            atomicAdd(a + 3, (unsigned)__popc(rb) + ((unsigned)euler << 20));       // pixel count < 2^20, Euler number mod 4096 above it
         }
     }
     gsync<NT>();
@@ -440,14 +462,25 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
     // ---- 6. keep blobs with non-zero polygon area (helpers.py:153), emit in reverse raster order
     unsigned n_keep = 0;
     {
-        unsigned carry = 0;
-        for (unsigned k0 = 0; k0 < nb; k0 += NT) {      // pass 1: count
+        unsigned carry = 0, holed = 0;
+        for (unsigned k0 = 0; k0 < nb; k0 += NT) {      // pass 1: count; a blob's Euler number is 1 - (number of holes)
             const unsigned k = k0 + tid;
             const unsigned keep = (k < nb && acc_get<WIDE>(sm.acc, 4 * k) != 0ull) ? 1u : 0u;
+            unsigned has_hole = 0;
+            if (k < nb) {
+                const unsigned long long a3 = acc_get<WIDE>(sm.acc, 4 * k + 3);
+                const int eu = WIDE ? (int)(long long)(a3 >> 32) : ((int)((unsigned)a3 >> 20) << 20) >> 20;      // sign-extended
+                has_hole = eu != 1 ? 1u : 0u;
+            }
             unsigned tot;
-            block_scan_excl<NT>(keep, tot, sm.wsum);
-            carry += tot;
+            block_scan_excl<NT>(keep | (has_hole << 16), tot, sm.wsum);
+            carry += tot & 0xffffu;
+            holed += tot >> 16;
         }
+        // cv.findContours(RETR_TREE) gives every hole a contour of its own (one more point, helpers.py:147-158) and
+        // the outer contour's moments are those of the FILLED blob: this path reports the set pixels' polygon and
+        // says so
+        if (holed) flags |= MOCAP_F_HOLES;
         n_keep = carry;
         carry = 0;
         for (unsigned k0 = 0; k0 < nb; k0 += NT) {      // pass 2: place
@@ -466,7 +499,8 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
                     out_xy[2 * o + 1] = (int)(m01 / m00);
                     if (out_mom) {
                         out_mom[4 * o + 0] = (int64_t)A2; out_mom[4 * o + 1] = (int64_t)SX6;
-                        out_mom[4 * o + 2] = (int64_t)SY6; out_mom[4 * o + 3] = (int64_t)acc_get<WIDE>(sm.acc, 4 * k + 3);
+                        out_mom[4 * o + 2] = (int64_t)SY6;
+                        out_mom[4 * o + 3] = (int64_t)(acc_get<WIDE>(sm.acc, 4 * k + 3) & (WIDE ? 0xffffffffull : 0xfffffull));
                     }
                 }
             }

@@ -78,9 +78,10 @@ __device__ __forceinline__ void finish_image(const FusedParams& P, unsigned char
         if (lane == 0) P.set_worklist[atomicAdd(P.set_work_count, 1u)] = (uint32_t)set;
         return;
     }
-    WarpState ws = carve_warp_state(slab, P.RMAX, P.C, P.KC);
+    WarpState ws = carve_warp_state(slab, P.RMAX, P.C, P.KC, P.MB);
     match_triangulate_warp(P.tb, ws, P.blob_xy + (size_t)set * P.C * P.MB * 2, P.blob_n + (size_t)set * P.C, set, lane,
-                           P.C, P.MB, P.RMAX, P.KC, P.GMAX, P.obj, P.err, P.n_obj, P.set_flags, nullptr, P.track_xy);
+                           P.C, P.MB, P.RMAX, P.KC, P.GMAX, P.obj, P.err, P.n_obj, P.set_flags, nullptr, P.track_xy,
+                           P.img_flags ? P.img_flags + (size_t)set * P.C : nullptr);
     __syncwarp();
 }
 

@@ -17,7 +17,7 @@
 #include "fused_phased.cuh"
 
 size_t fused_slab_bytes(const mocap_config& c) {
-    size_t a = sizeof(WarpSlab), b = warp_state_bytes(c.max_roots, c.n_cam, c.max_cands);
+    size_t a = sizeof(WarpSlab), b = warp_state_bytes(c.max_roots, c.n_cam, c.max_cands, c.max_blobs);
     size_t m = a > b ? a : b;
     return (m + 15) & ~(size_t)15;
 }

@@ -181,9 +181,10 @@ k_pipeline_phased(const FusedParams P) {
         if (match_now) {
             for (unsigned k = warp; k < ns; k += FUSED_WARPS) {
                 const int set = (int)q.set[k];
-                WarpState ws = carve_warp_state(slab, P.RMAX, P.C, P.KC);
+                WarpState ws = carve_warp_state(slab, P.RMAX, P.C, P.KC, P.MB);
                 match_triangulate_warp(P.tb, ws, P.blob_xy + (size_t)set * P.C * P.MB * 2, P.blob_n + (size_t)set * P.C, set, lane,
-                                       P.C, P.MB, P.RMAX, P.KC, P.GMAX, P.obj, P.err, P.n_obj, P.set_flags, nullptr, P.track_xy);
+                                       P.C, P.MB, P.RMAX, P.KC, P.GMAX, P.obj, P.err, P.n_obj, P.set_flags, nullptr, P.track_xy,
+                                       P.img_flags ? P.img_flags + (size_t)set * P.C : nullptr);
                 __syncwarp();
             }
         }

@@ -176,7 +176,7 @@ GEOM_HD bool sym4_null_vector_invit(const Sym4& B, double out[4]) {
     if (fabs(d3) < 1e-290) d3 = 1e-290;                 // exactly singular data: any huge amplification will do
     const double i3 = 1.0 / d3;
     double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 1.0;
-    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 1.0;
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 1.0, pm = 1.0;
     bool settled = false;
     for (int it = 0; it < 40; ++it) {
         // L z = y ; z /= d ; L^T y' = z
@@ -188,21 +188,29 @@ GEOM_HD bool sym4_null_vector_invit(const Sym4& B, double out[4]) {
         // renormalise by an exact power of two (keeps the iterates in range without rounding)
         const double m = fmax(fmax(fabs(w0), fabs(w1)), fmax(fabs(w2), fabs(w3)));
         if (!(m > 0.0) || !(m < 1e300)) return false;
+#if defined(__CUDA_ARCH__)
+        // 2^-e with e = frexp's exponent, straight from the exponent field (m is a normal number here, or so small
+        // that the iteration is about to be abandoned anyway): one multiply per component instead of frexp + 4 ldexp
+        const int ebits = (__double2hiint(m) >> 20) & 0x7ff;
+        const double sc2 = __hiloint2double((2045 - ebits) << 20, 0);
+        y0 = w0 * sc2; y1 = w1 * sc2; y2 = w2 * sc2; y3 = w3 * sc2;
+        const double ym = m * sc2;
+#else
         int e;
         (void)frexp(m, &e);
         y0 = ldexp(w0, -e); y1 = ldexp(w1, -e); y2 = ldexp(w2, -e); y3 = ldexp(w3, -e);
+        const double ym = ldexp(m, -e);
+#endif
         if (it >= 2) {
-            // direction change since the previous iterate, sign-insensitive: |y x p| components vs |y||p|
+            // direction change since the previous iterate, sign-insensitive and division-free:
+            // y ~ sg (ym / pm) p when settled  <=>  |y pm - sg ym p| small against ym pm   (ym, pm in [0.5, 1))
             const double dot = y0 * p0 + y1 * p1 + y2 * p2 + y3 * p3;
-            const double sg = dot < 0.0 ? -1.0 : 1.0;
-            const double pm = fmax(fmax(fabs(p0), fabs(p1)), fmax(fabs(p2), fabs(p3)));   // both in [0.5, 1)
-            const double ym = fmax(fmax(fabs(y0), fabs(y1)), fmax(fabs(y2), fabs(y3)));
-            const double sc = ym / pm;                   // y ~ sc * sg * p when settled
-            const double dev = fmax(fmax(fabs(y0 - sg * sc * p0), fabs(y1 - sg * sc * p1)),
-                                    fmax(fabs(y2 - sg * sc * p2), fabs(y3 - sg * sc * p3)));
-            if (dev <= 2e-14 * ym) { settled = true; break; }
+            const double sy = dot < 0.0 ? -ym : ym;
+            const double dev = fmax(fmax(fabs(y0 * pm - sy * p0), fabs(y1 * pm - sy * p1)),
+                                    fmax(fabs(y2 * pm - sy * p2), fabs(y3 * pm - sy * p3)));
+            if (dev <= 2e-14 * (ym * pm)) { settled = true; break; }
         }
-        p0 = y0; p1 = y1; p2 = y2; p3 = y3;
+        p0 = y0; p1 = y1; p2 = y2; p3 = y3; pm = ym;
     }
     if (!settled) return false;
     out[0] = y0; out[1] = y1; out[2] = y2; out[3] = y3;

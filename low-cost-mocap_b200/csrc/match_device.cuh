@@ -16,28 +16,31 @@ struct WarpState {
     unsigned long long* best_key;  // [RMAX]
     uint32_t* best_g;  // [RMAX]
     double* best_xe;   // [RMAX][4]  X and error of the best group so far
+    int32_t* xy_s;     // [C][MB][2] the frame-set's blob centres, staged once (every later read is a shared-memory load)
 };
 
-static __host__ __device__ size_t warp_state_bytes(int RMAX, int C, int KC) {
+static __host__ __device__ size_t warp_state_bytes(int RMAX, int C, int KC, int MB) {
     size_t b = 0;
     b += (size_t)RMAX * 32;                      // best_xe
     b += (size_t)RMAX * 8;                       // best_key
     b += (size_t)RMAX * 4 * 2 + (RMAX + 1) * 4;  // gcount, best_g, gprefix
+    b += (size_t)C * MB * 8;                     // xy_s
     b += (size_t)RMAX * 2;                       // rcam, rpt
     b += (size_t)RMAX * C;                       // ncand
     b += (size_t)RMAX * C * KC;                  // cand
     return (b + 15) & ~(size_t)15;
 }
 inline size_t match_smem_bytes(const mocap_config& cfg, int warps) {
-    return warp_state_bytes(cfg.max_roots, cfg.n_cam, cfg.max_cands) * warps;
+    return warp_state_bytes(cfg.max_roots, cfg.n_cam, cfg.max_cands, cfg.max_blobs) * warps;
 }
-__device__ __forceinline__ WarpState carve_warp_state(unsigned char* raw, int RMAX, int C, int KC) {
+__device__ __forceinline__ WarpState carve_warp_state(unsigned char* raw, int RMAX, int C, int KC, int MB) {
     WarpState s;
     s.best_xe = reinterpret_cast<double*>(raw);              raw += (size_t)RMAX * 32;
     s.best_key = reinterpret_cast<unsigned long long*>(raw); raw += (size_t)RMAX * 8;
     s.gcount = reinterpret_cast<uint32_t*>(raw);             raw += (size_t)RMAX * 4;
     s.best_g = reinterpret_cast<uint32_t*>(raw);             raw += (size_t)RMAX * 4;
     s.gprefix = reinterpret_cast<uint32_t*>(raw);            raw += (size_t)(RMAX + 1) * 4;
+    s.xy_s = reinterpret_cast<int32_t*>(raw);                raw += (size_t)C * MB * 8;
     s.rcam = raw;                                            raw += RMAX;
     s.rpt = raw;                                             raw += RMAX;
     s.ncand = raw;                                           raw += (size_t)RMAX * C;
@@ -84,8 +87,8 @@ static __device__ __noinline__ void eval_group(const CameraTables* __restrict__ 
 #pragma unroll 1
     for (int k = 0; k < nv; ++k) {
         const int c = cams[k];
-        const double px = (double)__ldcg(xy + ((size_t)c * MB + pts[k]) * 2 + 0);
-        const double py = (double)__ldcg(xy + ((size_t)c * MB + pts[k]) * 2 + 1);
+        const double px = (double)xy[((size_t)c * MB + pts[k]) * 2 + 0];
+        const double py = (double)xy[((size_t)c * MB + pts[k]) * 2 + 1];
         dlt_add_view(B, tb->Pkc[k][c], px, py);      // K of the k-th PRESENT view (helpers.py:305-307)
     }
     dlt_solve(B, X);
@@ -95,8 +98,8 @@ static __device__ __noinline__ void eval_group(const CameraTables* __restrict__ 
         const int c = cams[k];
         float u, v;
         project_like_cv(tb->R[c], tb->t[c], tb->fx[k], tb->fy[k], tb->cx[k], tb->cy[k], X, u, v);
-        const double dx = DSUB((double)__ldcg(xy + ((size_t)c * MB + pts[k]) * 2 + 0), (double)u);
-        const double dy = DSUB((double)__ldcg(xy + ((size_t)c * MB + pts[k]) * 2 + 1), (double)v);
+        const double dx = DSUB((double)xy[((size_t)c * MB + pts[k]) * 2 + 0], (double)u);
+        const double dy = DSUB((double)xy[((size_t)c * MB + pts[k]) * 2 + 1], (double)v);
         sq[2 * k] = DMUL(dx, dx);
         sq[2 * k + 1] = DMUL(dy, dy);
     }
@@ -111,8 +114,28 @@ static __device__ __noinline__ void match_triangulate_warp(
     const CameraTables* __restrict__ tb, WarpState ws, const int32_t* xy, const int32_t* nb, int set, int lane,
     int C, int MB, int RMAX, int KC, uint32_t GMAX, double* __restrict__ obj, double* __restrict__ err_out,
     int32_t* __restrict__ n_obj, int32_t* __restrict__ set_flags, int32_t* __restrict__ chosen,
-    int32_t* __restrict__ track_xy = nullptr) {
+    int32_t* __restrict__ track_xy = nullptr, const int32_t* img_flags = nullptr) {
     int flags = 0;
+    // inside a pipeline: what S1 reported for the frame-set's images (truncated blob lists, blobs with holes) travels
+    // with the frame-set
+    if (img_flags) {
+        int f = lane < C ? __ldcg(img_flags + lane) : 0;
+#pragma unroll 1
+        for (int o = 16; o > 0; o >>= 1) f |= __shfl_xor_sync(FULL_MASK, f, o);
+        flags = f;
+    }
+
+    // stage the blob centres of the frame-set's cameras (read with ld.global.cg: they may have been written earlier
+    // in the same kernel by other warps) -- the matcher re-reads them hundreds of times
+    {
+        const int32_t* gxy = xy;
+        for (int c = 0; c < C; ++c) {
+            const int k2 = 2 * min(__ldcg(nb + c), MB);
+            for (int q = lane; q < k2; q += 32) ws.xy_s[c * MB * 2 + q] = __ldcg(gxy + (size_t)c * MB * 2 + q);
+        }
+        __syncwarp();
+        xy = ws.xy_s;
+    }
 
     // roots from camera 0 (helpers.py:349,357)
     int nr = min(__ldcg(nb), MB);
@@ -128,8 +151,8 @@ static __device__ __noinline__ void match_triangulate_warp(
         unsigned long long matched = 0ull;                     // "closest match" blobs of camera i
         for (int j = lane; j < nr; j += 32) {                  // roots that exist before camera i
             const int rc = ws.rcam[j];
-            const double rx = (double)__ldcg(xy + ((size_t)rc * MB + ws.rpt[j]) * 2 + 0);
-            const double ry = (double)__ldcg(xy + ((size_t)rc * MB + ws.rpt[j]) * 2 + 1);
+            const double rx = (double)xy[((size_t)rc * MB + ws.rpt[j]) * 2 + 0];
+            const double ry = (double)xy[((size_t)rc * MB + ws.rpt[j]) * 2 + 1];
             const double* F = tb->F[rc][i];
             // cv.computeCorrespondEpilines on a float32 point: double math, float32 result (helpers.py:363-364)
             double a = DADD(DADD(DMUL(F[0], rx), DMUL(F[1], ry)), F[2]);
@@ -146,8 +169,8 @@ static __device__ __noinline__ void match_triangulate_warp(
             int cnt = 0;
 #pragma unroll 1
             for (int q = 0; q < ni; ++q) {
-                const double px = (double)__ldcg(xy + ((size_t)i * MB + q) * 2 + 0);
-                const double py = (double)__ldcg(xy + ((size_t)i * MB + q) * 2 + 1);
+                const double px = (double)xy[((size_t)i * MB + q) * 2 + 0];
+                const double py = (double)xy[((size_t)i * MB + q) * 2 + 1];
                 const double d = fabs(DADD(DADD(DMUL(a, px), DMUL(b, py)), c)) / den;
                 if (d < 5.0) {                                  // helpers.py:375
                     if (cnt == KC) {
@@ -164,9 +187,9 @@ static __device__ __noinline__ void match_triangulate_warp(
             ws.ncand[j * C + i] = (uint8_t)cnt;
             if (cnt > 0) {                                      // helpers.py:391: drop every row equal to the closest match
                 const int q0 = cl[0];
-                const int cx0 = __ldcg(xy + ((size_t)i * MB + q0) * 2 + 0), cy0 = __ldcg(xy + ((size_t)i * MB + q0) * 2 + 1);
+                const int cx0 = xy[((size_t)i * MB + q0) * 2 + 0], cy0 = xy[((size_t)i * MB + q0) * 2 + 1];
                 for (int q = 0; q < ni; ++q)
-                    if (__ldcg(xy + ((size_t)i * MB + q) * 2 + 0) == cx0 && __ldcg(xy + ((size_t)i * MB + q) * 2 + 1) == cy0)
+                    if (xy[((size_t)i * MB + q) * 2 + 0] == cx0 && xy[((size_t)i * MB + q) * 2 + 1] == cy0)
                         matched |= 1ull << q;
             }
         }
@@ -273,8 +296,8 @@ static __device__ __noinline__ void match_triangulate_warp(
                 if (tx_s) {
                     for (int i = 0; i < 2 * C; ++i) tx_s[(size_t)o * C * 2 + i] = -1;
                     for (int k = 0; k < nv; ++k) {
-                        tx_s[((size_t)o * C + cams[k]) * 2 + 0] = __ldcg(xy + ((size_t)cams[k] * MB + pts[k]) * 2 + 0);
-                        tx_s[((size_t)o * C + cams[k]) * 2 + 1] = __ldcg(xy + ((size_t)cams[k] * MB + pts[k]) * 2 + 1);
+                        tx_s[((size_t)o * C + cams[k]) * 2 + 0] = xy[((size_t)cams[k] * MB + pts[k]) * 2 + 0];
+                        tx_s[((size_t)o * C + cams[k]) * 2 + 1] = xy[((size_t)cams[k] * MB + pts[k]) * 2 + 1];
                     }
                 }
             }

@@ -23,17 +23,18 @@ k_match_triangulate(const CameraTables* __restrict__ tb, const int32_t* blob_xy,
                     int n_sets, int C, int MB, int RMAX, int KC,
                     uint32_t GMAX, double* __restrict__ obj, double* __restrict__ err_out,
                     int32_t* __restrict__ n_obj, int32_t* __restrict__ set_flags, int32_t* __restrict__ chosen,
-                    int32_t* __restrict__ track_xy) {
+                    int32_t* __restrict__ track_xy, const int32_t* __restrict__ img_flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warps = blockDim.x >> 5;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpState ws = carve_warp_state(smem_raw + warp_state_bytes(RMAX, C, KC) * wid, RMAX, C, KC);
+    WarpState ws = carve_warp_state(smem_raw + warp_state_bytes(RMAX, C, KC, MB) * wid, RMAX, C, KC, MB);
     if (set_list) {                                   // persistent walk over a worklist of frame-sets
         const unsigned n_work = *set_count;
         for (unsigned w = blockIdx.x * warps + wid; w < n_work; w += gridDim.x * warps) {
             const int set = (int)set_list[w];
             match_triangulate_warp(tb, ws, blob_xy + (size_t)set * C * MB * 2, blob_n + (size_t)set * C, set, lane,
-                                   C, MB, RMAX, KC, GMAX, obj, err_out, n_obj, set_flags, chosen, track_xy);
+                                   C, MB, RMAX, KC, GMAX, obj, err_out, n_obj, set_flags, chosen, track_xy,
+                                   img_flags ? img_flags + (size_t)set * C : nullptr);
             __syncwarp();
         }
         __syncthreads();
@@ -46,7 +47,8 @@ k_match_triangulate(const CameraTables* __restrict__ tb, const int32_t* blob_xy,
     const int set = blockIdx.x * warps + wid;
     if (set >= n_sets) return;
     match_triangulate_warp(tb, ws, blob_xy + (size_t)set * C * MB * 2, blob_n + (size_t)set * C, set, lane,
-                           C, MB, RMAX, KC, GMAX, obj, err_out, n_obj, set_flags, chosen, track_xy);
+                           C, MB, RMAX, KC, GMAX, obj, err_out, n_obj, set_flags, chosen, track_xy,
+                           img_flags ? img_flags + (size_t)set * C : nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -107,7 +109,7 @@ int launch_match(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n, 
     const int grid = (n_sets + warps - 1) / warps;
     k_match_triangulate<<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_tables, blob_xy, blob_n, nullptr, nullptr, n_sets, c.n_cam,
                                                                  c.max_blobs, c.max_roots, c.max_cands,
-                                                                 (uint32_t)c.max_groups, obj, err, n_obj, set_flags, chosen, ctx->track_xy_cur);
+                                                                 (uint32_t)c.max_groups, obj, err, n_obj, set_flags, chosen, ctx->track_xy_cur, ctx->img_flags_cur);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 1;
     return MOCAP_OK;
@@ -122,7 +124,7 @@ int launch_match_list(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blo
     if (grid > ctx->num_sms) grid = ctx->num_sms;
     k_match_triangulate<<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_tables, blob_xy, blob_n, set_list, set_count, n_sets_max, c.n_cam,
                                                                  c.max_blobs, c.max_roots, c.max_cands, (uint32_t)c.max_groups,
-                                                                 obj, err, n_obj, set_flags, nullptr, ctx->track_xy_cur);
+                                                                 obj, err, n_obj, set_flags, nullptr, ctx->track_xy_cur, ctx->d_img_flags);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 1;
     return MOCAP_OK;

@@ -53,7 +53,7 @@ extern "C" int hc_pipeline_fused(const uint8_t* frames, int n_sets, int C, int W
     P.tb = &T;
     P.MB = MB; P.RMAX = RMAX; P.KC = KC; P.GMAX = GMAX;
     P.obj = obj; P.err = err; P.n_obj = n_obj; P.set_flags = set_flags;
-    const size_t a = sizeof(WarpSlab), b = warp_state_bytes(RMAX, C, KC);
+    const size_t a = sizeof(WarpSlab), b = warp_state_bytes(RMAX, C, KC, MB);
     P.slab_bytes = ((a > b ? a : b) + 15) & ~(size_t)15;
     if (phased) n_warps = FUSED_WARPS;                       // the phased kernel's loops are written for exactly this many warps
     if (P.slab_bytes * n_warps + sizeof(PhasedQueues) > sizeof(smem_raw)) return -1;

@@ -14,10 +14,10 @@ extern "C" int hc_match_triangulate(const double* K, const double* R, const doub
     static CameraTables T;                                   // 70 KB: not on the stack
     memset(&T, 0, sizeof(T));
     build_camera_tables(T, C, K, R, t);
-    std::vector<unsigned long long> raw(warp_state_bytes(RMAX, C, KC) / 8 + 2);
+    std::vector<unsigned long long> raw(warp_state_bytes(RMAX, C, KC, MB) / 8 + 2);
     for (int set = 0; set < n_sets; ++set) {
         simt::launch(32, [&] {
-            WarpState ws = carve_warp_state(reinterpret_cast<unsigned char*>(raw.data()), RMAX, C, KC);
+            WarpState ws = carve_warp_state(reinterpret_cast<unsigned char*>(raw.data()), RMAX, C, KC, MB);
             match_triangulate_warp(&T, ws, blob_xy + (size_t)set * C * MB * 2, blob_n + (size_t)set * C, set, (int)(threadIdx.x & 31),
                                    C, MB, RMAX, KC, GMAX, obj, err, n_obj, flags, nullptr);
         });

@@ -521,3 +521,47 @@ def test_ba_kernel_on_host_with_prefit_beats_the_reference(ba_emu):
     assert r1["status"] in (1, 2, 3, 4) and r1["smem"] < 227 * 1024
     assert abs(r1["cost_final"] - r2["cost_final"]) < 1e-6 and np.abs(R1 - R2).max() < 1e-7 and np.abs(t1 - t2).max() < 1e-7
     assert np.allclose(R1[0], np.eye(3)) and np.allclose(t1[0], 0)
+
+
+def test_blob_device_code_flags_blobs_with_holes(blob_emu):
+    """cv.findContours(RETR_TREE) (helpers.py:147) emits a contour per hole; the device code reports one centre per
+    blob and must say so: MOCAP_F_HOLES is set exactly for the images in which cv2 finds a hole contour.  Random
+    blobs (rings, blobs with several holes, nested blobs, holes touching diagonally, 1-px walls, blobs across the
+    16-px segment boundaries and at the image border), both variants of the device function."""
+    import cv2
+    rng = np.random.default_rng(31)
+    H, W = 96, 128
+    seen = {True: 0, False: 0}
+    for trial in range(60):
+        img = np.zeros((H, W), np.uint8)
+        for _ in range(rng.integers(1, 6)):
+            cx, cy = int(rng.integers(0, W)), int(rng.integers(0, H))
+            kind = rng.integers(0, 5)
+            if kind == 0:
+                cv2.circle(img, (cx, cy), int(rng.integers(2, 9)), 255, int(rng.integers(1, 3)))          # ring
+            elif kind == 1:
+                cv2.circle(img, (cx, cy), int(rng.integers(1, 7)), 255, -1)                                # disc
+            elif kind == 2:
+                w, h = int(rng.integers(3, 24)), int(rng.integers(3, 12))
+                cv2.rectangle(img, (cx, cy), (cx + w, cy + h), 255, 1)                                     # frame (may cross segments)
+                if rng.integers(0, 2):
+                    cv2.circle(img, (cx + w // 2, cy + h // 2), 1, 255, -1)                                # nested blob
+            elif kind == 3:
+                m = (rng.uniform(size=(9, 14)) < 0.72).astype(np.uint8) * 255                              # porous patch
+                y0, x0 = min(cy, H - 9), min(cx, W - 14)
+                img[y0:y0 + 9, x0:x0 + 14] = np.maximum(img[y0:y0 + 9, x0:x0 + 14], m)
+            else:
+                img[max(cy - 2, 0):cy + 3, max(cx - 2, 0):cx + 3] = 255
+                img[cy, cx] = 0 if rng.integers(0, 2) else 255                                            # 1-px hole
+        contours, hier = cv2.findContours((img > 51).astype(np.uint8), cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+        if hier is None:
+            continue
+        # with RETR_TREE the contours at odd nesting depth are the hole borders
+        depth = lambda i: 0 if hier[0][i][3] < 0 else 1 + depth(hier[0][i][3])
+        has_hole = any(depth(i) % 2 == 1 for i in range(len(contours)))
+        seen[has_hole] += 1
+        for force_cta in (0, 1):
+            d = blob_emu(img, force_cta=force_cta, seed=trial)
+            assert bool(d["flags"] & 32) == has_hole, (trial, force_cta, d["flags"])
+            assert d["flags"] & ~32 == 0
+    assert seen[True] >= 15 and seen[False] >= 5
