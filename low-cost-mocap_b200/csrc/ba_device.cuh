@@ -227,17 +227,15 @@ BA_DEV void ba_exp_so3(const double w[3], double E[9]) {
 // In place Cholesky of the lower triangle.  *flag (shared) is 1 on entry; 0 on exit if not positive definite.
 BA_DEV bool ba_chol_factor(double* L, int n, int* flag) {
     const int tid = threadIdx.x, nt = blockDim.x;
+    (void)flag;
     for (int j = 0; j < n; ++j) {
-        __syncthreads();
-        if (tid == 0) {
-            const double d = L[j * n + j];
-            if (!(d > 0.0)) *flag = 0; else L[j * n + j] = sqrt(d);
-        }
-        __syncthreads();
-        if (!*flag) return false;
-        const double dj = L[j * n + j];
+        __syncthreads();                                           // column j has all its updates
+        const double d = L[j * n + j];                             // every thread reads the same pivot: a uniform decision
+        if (!(d > 0.0)) return false;
+        const double dj = sqrt(d);
         for (int i = j + 1 + tid; i < n; i += nt) L[i * n + j] /= dj;
-        __syncthreads();
+        __syncthreads();                                           // everybody has read the pivot; column j is scaled
+        if (tid == 0) L[j * n + j] = dj;
         const int cnt = n - j - 1;
         for (int idx = tid; idx < cnt * cnt; idx += nt) {
             const int ii = idx / cnt, kk = idx - ii * cnt;

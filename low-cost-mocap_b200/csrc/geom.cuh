@@ -150,70 +150,100 @@ GEOM_HD void sym4_null_vector(const Sym4& B, double out[4]) {
         out[r] = best == 0 ? v[r][0] : best == 1 ? v[r][1] : best == 2 ? v[r][2] : v[r][3];
 }
 
-// Fast path for the same null vector: inverse iteration on the LDL^T factors of B.  B = A^T A has one
-// eigenvalue far below the rest whenever the views agree on a point, so y <- B^-1 y converges to the
-// wanted eigenvector at the rate lambda4/lambda3 per step (typically 1e-3 .. 1e-6); rounding errors of
-// the ill-conditioned solves fall along that very eigenvector and are harmless.  Returns false -- and the
-// caller falls back to the Jacobi solver above -- when B is not numerically positive definite in its
-// leading 3x3 block or the iteration has not settled (near-degenerate geometry, lambda3 ~ lambda4).
-// ~25x fewer instructions than the Jacobi sweeps; the two agree to ~1e-13 relative.
-GEOM_HD bool sym4_null_vector_invit(const Sym4& B, double out[4]) {
-    const double b00 = B.v[0], b01 = B.v[1], b02 = B.v[2], b03 = B.v[3], b11 = B.v[4], b12 = B.v[5], b13 = B.v[6];
-    const double b22 = B.v[7], b23 = B.v[8], b33 = B.v[9];
-    if (!(b00 > 0.0)) return false;
-    const double i0 = 1.0 / b00;
-    const double l10 = b01 * i0, l20 = b02 * i0, l30 = b03 * i0;
-    const double d1 = b11 - l10 * b01;
-    if (!(d1 > 1e-14 * b11)) return false;
-    const double i1 = 1.0 / d1;
-    const double l21 = (b12 - l20 * b01) * i1, l31 = (b13 - l30 * b01) * i1;
-    const double d2 = b22 - l20 * b02 - l21 * (l21 * d1);
-    if (!(d2 > 1e-14 * b22)) return false;
-    const double i2 = 1.0 / d2;
-    const double l32 = (b23 - l30 * b02 - l31 * (l21 * d1)) * i2;
-    double d3 = b33 - l30 * b03 - l31 * (l31 * d1) - l32 * (l32 * d2);
+// Fast path for the same null vector: two plain inverse-iteration steps on the LDL^T factors of B (they pull the
+// start vector towards the eigenvector of the smallest eigenvalue at the rate lambda4/lambda3 per step), then
+// Rayleigh-quotient iteration -- every step re-factors B - rho I with rho = y^T B y / y^T y and converges cubically,
+// so that candidate groups whose views do NOT agree on a point (lambda4/lambda3 near 1: most groups of a busy
+// frame-set) settle in the same handful of steps as the good ones and a warp's lanes stay together.  The iteration
+// stops when two successive iterates agree to 2e-14.  Because a Rayleigh quotient can be drawn to lambda3 when
+// the two smallest eigenvalues are close, the result is accepted only if B - (rho - delta) I is positive definite
+// (no eigenvalue below rho: pivot signs of one more LDL^T, delta = 1e-9 trace(B)); otherwise -- and whenever a
+// pivot breaks down or nothing settles -- this returns false and the caller runs the Jacobi solver above.
+// The two agree to ~1e-13 relative.
+struct Ldl4 { double l10, l20, l30, l21, l31, l32, i0, i1, i2, i3; };
+
+// LDL^T of B - shift I without pivoting; false on a zero / non-finite pivot.  n_neg = number of negative pivots.
+GEOM_HD bool sym4_ldl(const Sym4& B, double shift, Ldl4& f, int& n_neg) {
+    const double b00 = B.v[0] - shift, b01 = B.v[1], b02 = B.v[2], b03 = B.v[3], b11 = B.v[4] - shift, b12 = B.v[5], b13 = B.v[6];
+    const double b22 = B.v[7] - shift, b23 = B.v[8], b33 = B.v[9] - shift;
+    if (!(b00 != 0.0)) return false;
+    f.i0 = 1.0 / b00;
+    f.l10 = b01 * f.i0; f.l20 = b02 * f.i0; f.l30 = b03 * f.i0;
+    const double d1 = b11 - f.l10 * b01;
+    if (!(d1 != 0.0)) return false;
+    f.i1 = 1.0 / d1;
+    f.l21 = (b12 - f.l20 * b01) * f.i1; f.l31 = (b13 - f.l30 * b01) * f.i1;
+    const double d2 = b22 - f.l20 * b02 - f.l21 * (f.l21 * d1);
+    if (!(d2 != 0.0)) return false;
+    f.i2 = 1.0 / d2;
+    f.l32 = (b23 - f.l30 * b02 - f.l31 * (f.l21 * d1)) * f.i2;
+    double d3 = b33 - f.l30 * b03 - f.l31 * (f.l31 * d1) - f.l32 * (f.l32 * d2);
     if (!(d3 == d3)) return false;
-    if (fabs(d3) < 1e-290) d3 = 1e-290;                 // exactly singular data: any huge amplification will do
-    const double i3 = 1.0 / d3;
-    double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 1.0;
-    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 1.0, pm = 1.0;
-    bool settled = false;
-    for (int it = 0; it < 40; ++it) {
-        // L z = y ; z /= d ; L^T y' = z
-        const double z0 = y0, z1 = y1 - l10 * z0, z2 = y2 - l20 * z0 - l21 * z1, z3 = y3 - l30 * z0 - l31 * z1 - l32 * z2;
-        const double w3 = z3 * i3;
-        const double w2 = z2 * i2 - l32 * w3;
-        const double w1 = z1 * i1 - l21 * w2 - l31 * w3;
-        const double w0 = z0 * i0 - l10 * w1 - l20 * w2 - l30 * w3;
-        // renormalise by an exact power of two (keeps the iterates in range without rounding)
-        const double m = fmax(fmax(fabs(w0), fabs(w1)), fmax(fabs(w2), fabs(w3)));
-        if (!(m > 0.0) || !(m < 1e300)) return false;
+    if (fabs(d3) < 1e-290) d3 = 1e-290;                 // exactly singular: any huge amplification along the null vector will do
+    f.i3 = 1.0 / d3;
+    n_neg = (b00 < 0.0) + (d1 < 0.0) + (d2 < 0.0) + (d3 < 0.0);
+    return true;
+}
+
+// y <- normalised (B - shift I)^-1 y through the factors; ym = max |y_i| afterwards (in [0.5, 1)); false if it overflowed
+GEOM_HD bool sym4_invit_step(const Ldl4& f, double y[4], double& ym) {
+    const double z0 = y[0], z1 = y[1] - f.l10 * z0, z2 = y[2] - f.l20 * z0 - f.l21 * z1, z3 = y[3] - f.l30 * z0 - f.l31 * z1 - f.l32 * z2;
+    const double w3 = z3 * f.i3;
+    const double w2 = z2 * f.i2 - f.l32 * w3;
+    const double w1 = z1 * f.i1 - f.l21 * w2 - f.l31 * w3;
+    const double w0 = z0 * f.i0 - f.l10 * w1 - f.l20 * w2 - f.l30 * w3;
+    // renormalise by an exact power of two (keeps the iterates in range without rounding)
+    const double m = fmax(fmax(fabs(w0), fabs(w1)), fmax(fabs(w2), fabs(w3)));
+    if (!(m > 0.0) || !(m < 1e300)) return false;
 #if defined(__CUDA_ARCH__)
-        // 2^-e with e = frexp's exponent, straight from the exponent field (m is a normal number here, or so small
-        // that the iteration is about to be abandoned anyway): one multiply per component instead of frexp + 4 ldexp
-        const int ebits = (__double2hiint(m) >> 20) & 0x7ff;
-        const double sc2 = __hiloint2double((2045 - ebits) << 20, 0);
-        y0 = w0 * sc2; y1 = w1 * sc2; y2 = w2 * sc2; y3 = w3 * sc2;
-        const double ym = m * sc2;
+    // 2^-e with e = frexp's exponent, straight from the exponent field: one multiply per component
+    const int ebits = (__double2hiint(m) >> 20) & 0x7ff;
+    const double sc2 = __hiloint2double((2045 - ebits) << 20, 0);
+    y[0] = w0 * sc2; y[1] = w1 * sc2; y[2] = w2 * sc2; y[3] = w3 * sc2;
+    ym = m * sc2;
 #else
-        int e;
-        (void)frexp(m, &e);
-        y0 = ldexp(w0, -e); y1 = ldexp(w1, -e); y2 = ldexp(w2, -e); y3 = ldexp(w3, -e);
-        const double ym = ldexp(m, -e);
+    int e;
+    (void)frexp(m, &e);
+    y[0] = ldexp(w0, -e); y[1] = ldexp(w1, -e); y[2] = ldexp(w2, -e); y[3] = ldexp(w3, -e);
+    ym = ldexp(m, -e);
 #endif
-        if (it >= 2) {
-            // direction change since the previous iterate, sign-insensitive and division-free:
-            // y ~ sg (ym / pm) p when settled  <=>  |y pm - sg ym p| small against ym pm   (ym, pm in [0.5, 1))
-            const double dot = y0 * p0 + y1 * p1 + y2 * p2 + y3 * p3;
-            const double sy = dot < 0.0 ? -ym : ym;
-            const double dev = fmax(fmax(fabs(y0 * pm - sy * p0), fabs(y1 * pm - sy * p1)),
-                                    fmax(fabs(y2 * pm - sy * p2), fabs(y3 * pm - sy * p3)));
-            if (dev <= 2e-14 * (ym * pm)) { settled = true; break; }
-        }
-        p0 = y0; p1 = y1; p2 = y2; p3 = y3; pm = ym;
+    return true;
+}
+
+GEOM_HD bool sym4_null_vector_invit(const Sym4& B, double out[4]) {
+    Ldl4 f;
+    int n_neg = 0;
+    if (!(B.v[0] > 0.0)) return false;
+    if (!sym4_ldl(B, 0.0, f, n_neg) || n_neg != 0) return false;          // B = A^T A must be (numerically) positive definite
+    double y[4] = {0.0, 0.0, 0.0, 1.0}, ym = 1.0;
+    if (!sym4_invit_step(f, y, ym)) return false;
+    if (!sym4_invit_step(f, y, ym)) return false;
+    double p0 = y[0], p1 = y[1], p2 = y[2], p3 = y[3], pm = ym, rho = 0.0;
+    bool settled = false;
+#pragma unroll 1
+    for (int it = 0; it < 12; ++it) {
+        // Rayleigh quotient of the current iterate
+        const double q0 = B.v[0] * y[0] + B.v[1] * y[1] + B.v[2] * y[2] + B.v[3] * y[3];
+        const double q1 = B.v[1] * y[0] + B.v[4] * y[1] + B.v[5] * y[2] + B.v[6] * y[3];
+        const double q2 = B.v[2] * y[0] + B.v[5] * y[1] + B.v[7] * y[2] + B.v[8] * y[3];
+        const double q3 = B.v[3] * y[0] + B.v[6] * y[1] + B.v[8] * y[2] + B.v[9] * y[3];
+        rho = (y[0] * q0 + y[1] * q1 + y[2] * q2 + y[3] * q3) / (y[0] * y[0] + y[1] * y[1] + y[2] * y[2] + y[3] * y[3]);
+        if (!sym4_ldl(B, rho, f, n_neg)) return false;
+        if (!sym4_invit_step(f, y, ym)) return false;
+        // direction change since the previous iterate, sign-insensitive and division-free:
+        // y ~ sg (ym / pm) p when settled  <=>  |y pm - sg ym p| small against ym pm   (ym, pm in [0.5, 1))
+        const double dot = y[0] * p0 + y[1] * p1 + y[2] * p2 + y[3] * p3;
+        const double sy = dot < 0.0 ? -ym : ym;
+        const double dev = fmax(fmax(fabs(y[0] * pm - sy * p0), fabs(y[1] * pm - sy * p1)),
+                                fmax(fabs(y[2] * pm - sy * p2), fabs(y[3] * pm - sy * p3)));
+        p0 = y[0]; p1 = y[1]; p2 = y[2]; p3 = y[3]; pm = ym;
+        if (dev <= 2e-14 * (ym * pm)) { settled = true; break; }
     }
     if (!settled) return false;
-    out[0] = y0; out[1] = y1; out[2] = y2; out[3] = y3;
+    // the smallest eigenvalue?  (rho is the shift the last step was taken with: within O(dev) of the eigenvalue)
+    const double delta = 1e-9 * (B.v[0] + B.v[4] + B.v[7] + B.v[9]);
+    if (!sym4_ldl(B, rho - delta, f, n_neg) || n_neg != 0) return false;
+    out[0] = y[0]; out[1] = y[1]; out[2] = y[2]; out[3] = y[3];
     return true;
 }
 

@@ -117,6 +117,57 @@ def irregular_blob_case(name, n_frames, seed):
     print(name, "blobs/frame", blob_n.mean())
 
 
+def ring_blob_case(name, n_frames, seed):
+    """S1 on blobs WITH holes (rings, frames, porous patches, nested blobs) next to solid ones: what the real
+    _find_dot returns (one extra point per hole contour, hole-filled outer moments) and, per frame, whether cv2's
+    contour hierarchy contains a hole.  The CUDA path does not reproduce RETR_TREE on such blobs; it must raise
+    MOCAP_F_HOLES exactly on these frames and agree exactly on the others."""
+    import cv2
+    helpers, cams = load_reference(1)
+    rng = np.random.default_rng(seed)
+    H, W = synth.HEIGHT, synth.WIDTH
+    frames = np.zeros((n_frames, H, W), dtype=np.uint8)
+    has_hole = np.zeros((n_frames,), dtype=np.uint8)
+    for f in range(n_frames):
+        img = frames[f]
+        solid_only = f % 3 == 0
+        for _ in range(rng.integers(6, 20)):
+            cx, cy = int(rng.integers(20, W - 40)), int(rng.integers(20, H - 30))
+            kind = int(rng.integers(0, 5))
+            if kind == 0 and not solid_only:
+                cv2.circle(img, (cx, cy), int(rng.integers(3, 10)), 255, int(rng.integers(1, 3)))
+            elif kind == 1:
+                cv2.circle(img, (cx, cy), int(rng.integers(1, 7)), 230, -1)
+            elif kind == 2 and not solid_only:
+                w, h = int(rng.integers(3, 30)), int(rng.integers(3, 14))
+                cv2.rectangle(img, (cx, cy), (cx + w, cy + h), 255, 1)
+                if rng.integers(0, 2):
+                    cv2.circle(img, (cx + w // 2, cy + h // 2), 1, 255, -1)
+            elif kind == 3 and not solid_only:
+                m = (rng.uniform(size=(9, 14)) < 0.75).astype(np.uint8) * 200
+                img[cy:cy + 9, cx:cx + 14] = np.maximum(img[cy:cy + 9, cx:cx + 14], m)
+            else:
+                img[cy - 2:cy + 3, cx - 2:cx + 3] = 255
+    clean = frames.copy()
+    frames = synth.add_clutter(clean, 40, salt=seed)
+    blob_xy = np.full((n_frames, 1, 4 * MAXB, 2), -1, dtype=np.int32)
+    blob_n = np.zeros((n_frames, 1), dtype=np.int32)
+    for f in range(n_frames):
+        img3 = np.repeat(frames[f][:, :, None], 3, axis=2).copy()
+        _, pts = cams._find_dot(img3)
+        real = [p for p in pts if p[0] is not None]
+        blob_n[f, 0] = len(real)
+        for i, p in enumerate(real):
+            blob_xy[f, 0, i] = p
+        _, hier = cv2.findContours((frames[f] > 51).astype(np.uint8), cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+        if hier is not None:
+            depth = lambda i: 0 if hier[0][i][3] < 0 else 1 + depth(hier[0][i][3])
+            has_hole[f] = any(depth(i) % 2 == 1 for i in range(hier.shape[1]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), frames_clean=clean[:, None], clutter_max=40, clutter_salt=seed,
+                        blob_xy=blob_xy, blob_n=blob_n, has_hole=has_hole)
+    print(name, "blobs/frame", blob_n.mean(), "frames with holes", int(has_hole.sum()), "of", n_frames)
+
+
 def triangulate_case(name, C, F, seed):
     helpers, cams = load_reference(C)
     obs, poses, K, pts = synth.make_tracks(C, F, seed=seed)
@@ -162,13 +213,17 @@ def ba_case(name, C, F, seed):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pipe", "blobs", "tri", "ba"]
+    which = sys.argv[1:] or ["pipe", "blobs", "rings", "tri", "ba"]
+    if "pipe8" in which:
+        pipeline_case("pipe_c8_m16", 8, 16, 100, seed=0)
     if "pipe" in which:
         pipeline_case("pipe_c2_m1", 2, 1, 100, seed=0)      # BASELINE config 1 shape
         pipeline_case("pipe_c4_m4", 4, 4, 40, seed=0)      # config 2 shape
-        pipeline_case("pipe_c8_m16", 8, 16, 10, seed=0)    # config 3/4 shape
+        pipeline_case("pipe_c8_m16", 8, 16, 100, seed=0)   # config 3/4 shape (the first 10 frame-sets are those of the 10-set round-1 file)
     if "blobs" in which:
         irregular_blob_case("blobs_irregular", 30, seed=3)
+    if "rings" in which:
+        ring_blob_case("blobs_rings", 18, seed=4)
     if "tri" in which:
         triangulate_case("tri_c4", 4, 200, seed=5)
         triangulate_case("tri_c8", 8, 200, seed=6)

@@ -231,3 +231,23 @@ def test_install_into_reaches_the_names_index_imported_by_value(monkeypatch, syn
         for n, f in saved_i.items():
             setattr(index, n, f)
         type(cams)._find_dot = saved_fd
+
+
+@pytest.mark.parametrize("name", ["ba_c8", "ba_c16"])
+def test_port_residuals_equal_the_reference_run_golden(name):
+    """The larger S4 goldens (8 and 16 cameras) hold the start and the end state of a full bundle_adjustment run of
+    the REAL reference (7 and 25 minutes of CPU time, tests/golden/make_golden.py ba8 / ba16).  The port's residual
+    function must reproduce both residual vectors bit for bit."""
+    z = load_golden(name)
+    C = z["mask"].shape[1]
+    port = RefPort([z["K"]] * C)
+    obs = obs_from(z)
+    for tag in ("start", "final"):
+        poses = [{"R": z["R_" + tag][c], "t": z["t_" + tag][c]} for c in range(C)]
+        r = port.ba_residuals(port.poses_to_params(poses), obs)
+        ref = z["r0"] if tag == "start" else z["rf"]
+        if tag == "start":
+            assert np.array_equal(np.asarray(r, dtype=np.float32), ref)
+        else:                                       # R_final went through one more rotation-vector round trip
+            assert np.allclose(np.asarray(r, dtype=np.float32), ref, rtol=1e-5, atol=1e-6)
+    assert float(z["costf"]) < float(z["cost0"])

@@ -350,10 +350,14 @@ def _ref_cost(port, poses, obs_obj):
     return 0.5 * float(np.sum(np.log1p(r.astype(np.float64) ** 2))), r
 
 
-def test_ba_residual_vector_parity(torch):
+BA_GOLDEN = ["ba_c4", "ba_c8", "ba_c16"]       # 4 cameras x 40 points, 8 x 60 (config-3 rig), 16 x 96 (config-5 rig)
+
+
+@pytest.mark.parametrize("name", BA_GOLDEN)
+def test_ba_residual_vector_parity(torch, name):
     """SURVEY §7 level (i): the residual vector at identical parameters, after the same float32 cast."""
-    z = load_golden("ba_c4")
-    C = 4
+    z = load_golden(name)
+    C = z["mask"].shape[1]
     ctx = _ctx(C)
     start = [{"R": z["R_start"][c], "t": z["t_start"][c]} for c in range(C)]
     ctx.set_cameras([z["K"]] * C, start)
@@ -365,13 +369,16 @@ def test_ba_residual_vector_parity(torch):
     assert np.allclose(ctx.ba_residuals(z["obs"], z["mask"], final), z["rf"], rtol=1e-5, atol=1e-6)
 
 
-def test_ba_outcome_not_worse_than_reference(torch):
-    """SURVEY §7 level (ii): final robust cost <= the reference's on the same start; the returned
-    cost is re-computed with the oracle; re-triangulated points agree with the truth up to the
-    free global scale at least as well as the reference's result."""
+@pytest.mark.parametrize("name", BA_GOLDEN)
+def test_ba_outcome_not_worse_than_reference(torch, name):
+    """SURVEY §7 level (ii): final robust cost <= the reference's on the same start (the real reference's
+    bundle_adjustment run, golden); the returned cost is re-computed with the oracle; re-triangulated points agree
+    with the truth up to the free global scale at least as well as the reference's result; and continuing the
+    reference's own iteration from the returned poses does not lower the objective by more than its own stopping
+    tolerance (ftol = 1e-2), i.e. the polish was not stopped short."""
     from oracle.ref_port import RefPort
-    z = load_golden("ba_c4")
-    C = 4
+    z = load_golden(name)
+    C = z["mask"].shape[1]
     port = RefPort([z["K"]] * C)
     obs_obj = obs_from(z)
     ctx = _ctx(C)
@@ -394,6 +401,12 @@ def test_ba_outcome_not_worse_than_reference(torch):
         return np.abs(X * s - truth).max()
     ref_final = [{"R": z["R_final"][c], "t": z["t_final"][c]} for c in range(C)]
     assert scale_free_error(out) <= scale_free_error(ref_final) + 1e-9
+    assert rep["status"] in (1, 2, 3, 4) and np.isfinite(rep["optimality"])
+    # more of the reference's iteration (no prefit) from the result: nothing substantial left to gain
+    ctx.set_cameras([z["K"]] * C, out)
+    out2, rep2 = ctx.bundle_adjust(z["obs"], z["mask"], out, prefit=False)
+    assert rep2["cost_final"] >= rep["cost_final"] * (1.0 - 1e-2) - 1e-9
+    assert rep2["cost_final"] <= rep["cost_final"] * (1.0 + 1e-9) + 1e-12      # and it never gets worse
 
 
 def test_ba_reference_iteration_only(torch):
@@ -881,6 +894,45 @@ def test_matcher_fuzz_vs_oracle(torch):
                 assert np.allclose(err[b, :cnt[b]], e, rtol=1e-6, atol=1e-9)
 
 
+def test_matcher_heavy_fuzz_8_cameras(torch):
+    """The heavy regime of BASELINE configs 3/4: 8 cameras, 16-24 blobs per camera (16 markers seen by most cameras
+    plus clutter), candidate lists of up to 16 per epipolar line, hundreds of candidate groups per frame-set.  Kept
+    roots, their order, the chosen points and errors equal the oracle's; no capacity flag at max_cands = 16."""
+    from oracle.ref_port import RefPort
+    rng = np.random.default_rng(99)
+    C, B, MB = 8, 24, 32
+    poses, K = synth.make_rig(C)
+    port = RefPort([K] * C)
+    ctx = _ctx(C, max_blobs=MB, max_roots=128, max_cands=16, max_groups=1 << 16)
+    ctx.set_cameras([K] * C, poses)
+    xy = np.zeros((B, C, MB, 2), np.int32); n = np.zeros((B, C), np.int32)
+    for b in range(B):
+        pts3 = rng.uniform(-0.5, 0.5, size=(16, 3)) + np.array([0, 0, 3.0])
+        for c in range(C):
+            lst = [list(map(int, synth.project(p[None], poses[c], K)[0])) for p in pts3 if rng.uniform() < 0.9]
+            lst += [[int(rng.integers(100, 540)), int(rng.integers(100, 380))] for _ in range(int(rng.integers(2, 9)))]
+            seen, uniq = set(), []
+            for p in lst:
+                if tuple(p) not in seen and 0 <= p[0] < 640 and 0 <= p[1] < 480:
+                    seen.add(tuple(p)); uniq.append(p)
+            order = rng.permutation(len(uniq))
+            uniq = [uniq[i] for i in order][:MB]
+            n[b, c] = len(uniq)
+            xy[b, c, :len(uniq)] = uniq
+    assert n.mean() >= 16
+    d = ctx.match_triangulate(torch.from_numpy(xy.reshape(-1, MB, 2)).cuda(), torch.from_numpy(n.reshape(-1)).cuda())
+    cnt = d["n"].cpu().numpy(); obj = d["obj"].cpu().numpy(); err = d["err"].cpu().numpy()
+    assert (d["flags"].cpu().numpy() == 0).all()
+    for b in range(B):
+        lists = [[list(map(int, xy[b, c, i])) for i in range(n[b, c])] for c in range(C)]
+        e, o, _ = port.match_and_triangulate(lists, poses)
+        assert cnt[b] == len(e), b
+        ref = np.asarray(o, dtype=np.float64)
+        scale = np.maximum(1.0, np.abs(ref).max(axis=1, keepdims=True))
+        assert (np.abs(obj[b, :cnt[b]] - ref) / scale).max() <= 1e-6, b
+        assert np.allclose(err[b, :cnt[b]], e, rtol=1e-6, atol=1e-9)
+
+
 @pytest.mark.skipif(__import__("os").environ.get("MOCAP_TEST_TMA") != "1",
                     reason="experimental bulk-copy variant (not the default pipeline): run with MOCAP_TEST_TMA=1")
 def test_tma_pipeline_agrees_with_fused(torch, monkeypatch):
@@ -1149,3 +1201,41 @@ def test_config3_chain_on_the_device(torch):
     for c in range(C):
         assert np.abs(Rn[c] - np.asarray(poses[c]["R"])).max() < 5e-3
         assert np.abs(tn[c] * s - np.asarray(poses[c]["t"]).reshape(3)).max() < 2e-2
+
+
+def test_detect_flags_blobs_with_holes(torch):
+    """Blobs with holes (golden blobs_rings: rings, frames, porous patches, nested blobs through the REAL _find_dot):
+    cv.findContours(RETR_TREE) emits an extra contour per hole, this library does not -- MOCAP_F_HOLES must be set on
+    exactly the frames whose contour hierarchy has a hole, through mocap_detect_dev and through both pipelines (where
+    it travels into the frame-set flags); frames without holes agree with the reference exactly; the mirror raises."""
+    z = load_golden("blobs_rings")
+    frames = z["frames"]                                   # [F, 1, H, W]
+    F = frames.shape[0]
+    ctx = _ctx(1, max_blobs=64)
+    d = ctx.detect(torch.from_numpy(frames).cuda())
+    flags = d["flags"].cpu().numpy()
+    n = d["n"].cpu().numpy()
+    xy = d["xy"].cpu().numpy()
+    assert np.array_equal((flags & 32) != 0, z["has_hole"].astype(bool))
+    assert int(z["has_hole"].sum()) >= 5 and int((1 - z["has_hole"]).sum()) >= 5
+    for f in range(F):
+        if not z["has_hole"][f]:
+            k = int(z["blob_n"][f, 0])
+            assert flags[f] == 0 and n[f] == k and np.array_equal(xy[f, :k], z["blob_xy"][f, 0, :k]), f
+    ctx.set_cameras([np.array([[600.0, 0, 320], [0, 600, 240], [0, 0, 1]])], [{"R": np.eye(3), "t": np.zeros(3)}])
+    for mode in ("fused", "split"):
+        os.environ["MOCAP_PIPELINE"] = mode
+        try:
+            c2 = _ctx(1, max_blobs=64)
+        finally:
+            os.environ.pop("MOCAP_PIPELINE", None)
+        c2.set_cameras([np.array([[600.0, 0, 320], [0, 600, 240], [0, 0, 1]])], [{"R": np.eye(3), "t": np.zeros(3)}])
+        out = c2.pipeline(torch.from_numpy(frames).cuda())
+        assert np.array_equal((out["flags"].cpu().numpy() & 32) != 0, z["has_hole"].astype(bool)), mode
+    s = pkg.MocapSession([np.eye(3)])
+    holed = int(np.argmax(z["has_hole"]))
+    with pytest.raises(pkg.MocapError):
+        pkg.find_dot(as3(frames[holed, 0]), session=s)
+    solid = int(np.argmin(z["has_hole"]))
+    _, pts = pkg.find_dot(as3(frames[solid, 0]), session=s)
+    assert pts == z["blob_xy"][solid, 0, :int(z["blob_n"][solid, 0])].tolist()
