@@ -19,7 +19,12 @@
  *     "_host" entry points take HOST pointers, copy in/out and return when the
  *     results are in the host buffers.
  *   - one context per host thread (the reference's Cameras singleton is
- *     unsynchronised, Singleton.py:3); contexts are independent.
+ *     unsynchronised, Singleton.py:3); contexts are independent.  A context owns scratch
+ *     (segment lists, counters, blob lists) shared by all of its calls: use it from ONE
+ *     stream at a time -- before pointing it at another stream with mocap_set_stream, the
+ *     work already enqueued through it must have finished or be ordered before the new
+ *     stream's work (event).  The bundle-adjustment entry points use a workspace of their
+ *     own and may run on a second stream next to the pipeline entry points.
  *   - there is no CPU fallback: without a CUDA device every call fails with
  *     MOCAP_ENODEV.
  *
@@ -246,6 +251,8 @@ typedef struct mocap_ba_report {
     double prefit_cost_final;
     int    prefit_iterations;
     int    n_launches;     /* kernels launched by this call                            */
+    int    n_tr_solves;    /* device-resident solve: trust-region sub-problems solved, and ... */
+    int    n_tr_newton;    /* ... Newton iterations on the damping alpha they took in total (<= 10 each)  */
     float  phase_ms[8];    /* device-resident solve only: wall time per phase, CTA 0's clock --
                               0 set-up and control, 1 prefit: reduced camera system (Schur complement), 2 prefit: dense solve,
                               3 prefit: back-substitution + trial cost, 4 polish: finite-difference Jacobian + normal equations,

@@ -33,7 +33,8 @@ class BAReport(C.Structure):
     _fields_ = [("cost_initial", C.c_double), ("cost_final", C.c_double), ("optimality", C.c_double),
                 ("n_iterations", C.c_int), ("n_fev", C.c_int), ("status", C.c_int), ("n_residuals", C.c_int),
                 ("prefit_cost_initial", C.c_double), ("prefit_cost_final", C.c_double),
-                ("prefit_iterations", C.c_int), ("n_launches", C.c_int), ("phase_ms", C.c_float * 8)]
+                ("prefit_iterations", C.c_int), ("n_launches", C.c_int), ("n_tr_solves", C.c_int),
+                ("n_tr_newton", C.c_int), ("phase_ms", C.c_float * 8)]
 
 
 # every symbol include/mocap_b200.h declares: name -> (restype, argtypes)

@@ -301,7 +301,7 @@ struct BACtrl {
     double cost, cost_new, cost_initial, Delta, alpha, lambda, g_norm, pred, step_norm, actual, pcost, pcost_new;
     double pf_cost0, pf_cost1;
     double tr_alpha, tr_lower, tr_upper, tr_conv, a_diag, hh_beta, hh_alpha, hh_K;
-    int m, ntiles, n_valid, nfev, njev, iteration, termination, finite, flag, go, pf_it, accepted;
+    int m, ntiles, n_valid, nfev, njev, iteration, termination, finite, flag, go, pf_it, accepted, tr_its, tr_calls;
 };
 
 struct BAShared {
@@ -311,6 +311,7 @@ struct BAShared {
     double* colRt; int* colcam; double* dx;   // [n][12], [n], [n]
     double* g; double* p; double* q; double* w;   // [n]
     double* td; double* te; double* ghat; double* yhat; double* zhat; double* hv; double* hp; double* hu;   // [n] tridiagonal form of A
+    double* pcr;                       // [8][n] cyclic-reduction work arrays (two generations of a, b, c, d)
     uint8_t* pi; uint8_t* pj;          // [npair] pair -> (i, j), i <= j
     double* acc;                       // [pstride] this CTA's partial system
     double* scratch;                   // [threads] block sums
@@ -342,6 +343,7 @@ static __host__ __device__ inline size_t ba_smem_bytes(int C, int nt) {
     b += ba_align16((size_t)2 * C * 12 * 8);
     b += ba_align16((size_t)n * 12 * 8) + ba_align16((size_t)n * 4) + ba_align16((size_t)n * 8);
     b += 12 * ba_align16((size_t)n * 8);
+    b += ba_align16((size_t)8 * n * 8);
     b += 2 * ba_align16((size_t)npair);
     b += ba_align16((size_t)pstride * 8);
     b += ba_align16((size_t)nt * 8);
@@ -372,6 +374,7 @@ BA_DEV BAShared ba_carve(unsigned char* raw, int C, int nt) {
     s.hv = reinterpret_cast<double*>(raw); raw += ba_align16((size_t)n * 8);
     s.hp = reinterpret_cast<double*>(raw); raw += ba_align16((size_t)n * 8);
     s.hu = reinterpret_cast<double*>(raw); raw += ba_align16((size_t)n * 8);
+    s.pcr = reinterpret_cast<double*>(raw); raw += ba_align16((size_t)8 * n * 8);
     s.pi = raw; raw += ba_align16((size_t)npair);
     s.pj = raw; raw += ba_align16((size_t)npair);
     s.acc = reinterpret_cast<double*>(raw); raw += ba_align16((size_t)pstride * 8);
@@ -438,14 +441,19 @@ BA_DEV void ba_cost_pass(const BAParams& P, const BAShared& S, const double* Rt,
 }
 
 // publish 3 numbers of this CTA, grid barrier, read the grid totals (every CTA sums in CTA order)
-BA_DEV void ba_grid_sum3(const BAParams& P, int slot, const double v[3], double tot[3]) {
+BA_DEV void ba_grid_sum3(const BAParams& P, const BAShared& S, int slot, const double v[3], double tot[3]) {
     const int G = gridDim.x;
     double* cp = P.cpart + (size_t)slot * G * 4;
     if (threadIdx.x == 0) { cp[4 * blockIdx.x] = v[0]; cp[4 * blockIdx.x + 1] = v[1]; cp[4 * blockIdx.x + 2] = v[2]; }
     ba_grid_sync(P.bar);
-    double a = 0.0, b = 0.0, c = 0.0;                              // every thread the same sum, in CTA order
-    for (int g = 0; g < G; ++g) { a += __ldcg(cp + 4 * g); b += __ldcg(cp + 4 * g + 1); c += __ldcg(cp + 4 * g + 2); }
-    tot[0] = a; tot[1] = b; tot[2] = c;
+    if (threadIdx.x < 3) {                                         // one thread per component, in CTA order; the CTA shares the result
+        double a = 0.0;
+        for (int g = 0; g < G; ++g) a += __ldcg(cp + 4 * g + threadIdx.x);
+        S.scratch[threadIdx.x] = a;
+    }
+    __syncthreads();
+    tot[0] = S.scratch[0]; tot[1] = S.scratch[1]; tot[2] = S.scratch[2];
+    __syncthreads();
 }
 
 // write this CTA's partial system, grid barrier, add a slice of the entries over all CTAs, grid barrier
@@ -581,20 +589,37 @@ BA_DEV void ba_prefit_accumulate(const BAParams& P, const BAShared& S, double la
             }
         }
         __syncthreads();
-        // every thread updates the entries it owns
-        for (int k = tid; k < npair; k += nt) {
-            const int i = S.pi[k], j = S.pj[k];
-            double s = 0.0;
-            for (int r = 0; r < 3 * Pp; ++r) s -= Z[(size_t)r * n + i] * Z[(size_t)r * n + j];
-            if (i / 6 == j / 6) {
-                const int c = i / 6 + 1, a = i % 6, b2 = j % 6;
-                for (int pt = 0; pt < Pp; ++pt)
-                    if (pres[pt * C + c]) {
-                        const double* jc = Jc + ((size_t)pt * C + c) * 12;
-                        s += jc[a] * jc[b2] + jc[6 + a] * jc[6 + b2];
-                    }
+        // every thread updates the entries it owns: 2x2 blocks of (i, j) (n is even), so that a step over one row of Z
+        // costs two 16-byte shared-memory loads per four multiply-adds
+        {
+            const int nb2 = n / 2, nblk = nb2 * (nb2 + 1) / 2;
+            for (int blk = tid; blk < nblk; blk += nt) {
+                int bi = 0, rem = blk;
+                while (rem >= nb2 - bi) { rem -= nb2 - bi; ++bi; }
+                const int bj = bi + rem, i0 = 2 * bi, j0 = 2 * bj;
+                double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+                for (int r = 0; r < 3 * Pp; ++r) {
+                    const double2 zi = *reinterpret_cast<const double2*>(Z + (size_t)r * n + i0);
+                    const double2 zj = *reinterpret_cast<const double2*>(Z + (size_t)r * n + j0);
+                    a00 -= zi.x * zj.x; a01 -= zi.x * zj.y; a10 -= zi.y * zj.x; a11 -= zi.y * zj.y;
+                }
+                if (bi / 3 == bj / 3) {                           // same camera block: + Jc^T Jc
+                    const int c = bi / 3 + 1, a = i0 % 6, b2 = j0 % 6;
+                    for (int pt = 0; pt < Pp; ++pt)
+                        if (pres[pt * C + c]) {
+                            const double* jc = Jc + ((size_t)pt * C + c) * 12;
+                            a00 += jc[a] * jc[b2] + jc[6 + a] * jc[6 + b2];
+                            a01 += jc[a] * jc[b2 + 1] + jc[6 + a] * jc[6 + b2 + 1];
+                            a10 += jc[a + 1] * jc[b2] + jc[6 + a + 1] * jc[6 + b2];
+                            a11 += jc[a + 1] * jc[b2 + 1] + jc[6 + a + 1] * jc[6 + b2 + 1];
+                        }
+                }
+                const int k0 = i0 * n - i0 * (i0 - 1) / 2 + (j0 - i0);            // (i0, j0), (i0, j0 + 1) are neighbours in row i0
+                const int k1 = (i0 + 1) * n - (i0 + 1) * i0 / 2 + (j0 - i0 - 1);  // (i0 + 1, j0)
+                S.acc[k0] += a00; S.acc[k0 + 1] += a01;
+                S.acc[k1 + 1] += a11;
+                if (bi < bj) S.acc[k1] += a10;                    // below the diagonal inside a diagonal block
             }
-            S.acc[k] += s;
         }
         for (int i = tid; i < n; i += nt) {
             const int c = i / 6 + 1, a = i % 6;
@@ -877,65 +902,91 @@ BA_DEV void ba_tridiagonalise(const BAShared& S, int n) {
     __syncthreads();
 }
 
-// one thread: (T + alpha I) y = rhs through the LDL^T factors of the tridiagonal matrix (l in S.hp, 1/D in S.hu: the
-// pivots' reciprocals are the only dependent divisions); factor == true computes them first and returns false if
-// a pivot is not positive
-BA_DEV bool ba_tridiag_solve(const BAShared& S, int n, double alpha, bool factor, const double* rhs, double* y) {
-    double* l = S.hp;
-    double* Di = S.hu;
-    if (factor) {
-        double d = S.td[0] + alpha;
-        if (!(d > 0.0)) return false;
-        double di = 1.0 / d;
-        Di[0] = di;
-        for (int i = 0; i + 1 < n; ++i) {
-            const double e = S.te[i];
-            const double li = e * di;
-            l[i] = li;
-            d = (S.td[i + 1] + alpha) - li * e;
-            if (!(d > 0.0)) return false;
-            di = 1.0 / d;
-            Di[i + 1] = di;
-        }
+// sum over the warp of per-lane partial sums, fixed tree: every CTA gets the same bits
+BA_DEV double ba_warp_sum(double v) {
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// one WARP: (T + alpha I) x = rhs for the symmetric tridiagonal T = tridiag(S.td, S.te) by parallel cyclic reduction:
+// ceil(log2 n) steps, in each of which every equation i eliminates its neighbours i - s and i + s (two independent
+// divisions per equation), instead of a chain of n dependent pivots -- the trust-region sub-problem evaluates this
+// twice per Newton step on alpha and used to spend most of its time in that chain.  For a positive definite matrix
+// every diagonal entry stays positive (they are Schur complements); returns false (warp-uniform) if one does not.
+BA_DEV bool ba_pcr_solve(const BAShared& S, int n, double alpha, const double* rhs, double* x, int lane) {
+    double* buf = S.pcr;
+    int cur = 0;
+    for (int i = lane; i < n; i += 32) {
+        buf[0 * n + i] = i > 0 ? S.te[i - 1] : 0.0;               // a: sub-diagonal
+        buf[1 * n + i] = S.td[i] + alpha;                          // b: diagonal
+        buf[2 * n + i] = i + 1 < n ? S.te[i] : 0.0;                // c: super-diagonal
+        buf[3 * n + i] = rhs[i];
     }
-    double prev = rhs[0];
-    y[0] = prev;
-    for (int i = 0; i + 1 < n; ++i) { prev = rhs[i + 1] - l[i] * prev; y[i + 1] = prev; }
-    for (int i = 0; i < n; ++i) y[i] *= Di[i];
-    prev = y[n - 1];
-    for (int i = n - 2; i >= 0; --i) { prev = y[i] - l[i] * prev; y[i] = prev; }
-    return true;
+    __syncwarp();
+    bool ok = true;
+    for (int st = 1; st < n; st <<= 1) {
+        const double* A0 = buf + (size_t)(4 * cur + 0) * n; const double* B0 = buf + (size_t)(4 * cur + 1) * n;
+        const double* C0 = buf + (size_t)(4 * cur + 2) * n; const double* D0 = buf + (size_t)(4 * cur + 3) * n;
+        double* A1 = buf + (size_t)(4 * (cur ^ 1) + 0) * n; double* B1 = buf + (size_t)(4 * (cur ^ 1) + 1) * n;
+        double* C1 = buf + (size_t)(4 * (cur ^ 1) + 2) * n; double* D1 = buf + (size_t)(4 * (cur ^ 1) + 3) * n;
+        for (int i = lane; i < n; i += 32) {
+            const int im = i - st, ip = i + st;
+            double bb = B0[i], dd = D0[i], aa = 0.0, cc = 0.0;
+            if (!(bb > 0.0)) ok = false;
+            if (im >= 0) { const double k1 = A0[i] / B0[im]; bb -= C0[im] * k1; dd -= D0[im] * k1; aa = -A0[im] * k1; }
+            if (ip < n) { const double k2 = C0[i] / B0[ip]; bb -= A0[ip] * k2; dd -= D0[ip] * k2; cc = -C0[ip] * k2; }
+            A1[i] = aa; B1[i] = bb; C1[i] = cc; D1[i] = dd;
+        }
+        __syncwarp();
+        cur ^= 1;
+    }
+    const double* Bf = buf + (size_t)(4 * cur + 1) * n; const double* Df = buf + (size_t)(4 * cur + 3) * n;
+    for (int i = lane; i < n; i += 32) {
+        if (!(Bf[i] > 0.0)) ok = false;
+        x[i] = Df[i] / Bf[i];
+    }
+    ok = __ballot_sync(0xffffffffu, ok ? 0 : 1) == 0u;
+    __syncwarp();
+    return ok;
 }
 
 // scipy common.py solve_lsq_trust_region (rank-deficient branch, as the reference's dead focal parameters force):
 // step p of norm Delta minimising the quadratic model, iterated in the tridiagonal basis of ba_tridiagonalise:
 // phi(alpha) = |(T + alpha I)^-1 ghat| - Delta and phi'(alpha) = -y^T (T + alpha I)^-1 y / |y| are what scipy
-// evaluates from the singular values.  In: ctl->Delta, ctl->alpha.  Out: S.p, ctl->alpha, ctl->pred (the
-// predicted reduction -(0.5 p^T A p + g^T p)), ctl->step_norm.
+// evaluates from the singular values.  One warp runs the Newton iteration on alpha (every lane carries the same
+// scalars).  In: ctl->Delta, ctl->alpha.  Out: S.p, ctl->alpha, ctl->pred (the predicted reduction
+// -(0.5 p^T A p + g^T p)), ctl->step_norm.
 BA_DEV void ba_solve_tr(const BAShared& S, int n) {
     const int tid = threadIdx.x, nt = blockDim.x;
     BACtrl* ctl = S.ctl;
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {
+        const int lane = tid;
         const double Delta = ctl->Delta;
-        double upper = ba_norm2_serial(S.ghat, n) / Delta, lower = 0.0;
+        double part = 0.0;
+        for (int i = lane; i < n; i += 32) { part += S.ghat[i] * S.ghat[i]; S.q[i] = -S.ghat[i]; }
+        double upper = sqrt(ba_warp_sum(part)) / Delta, lower = 0.0;
         double alpha = ctl->alpha;
         if (alpha == 0.0) alpha = fmax(0.001 * upper, sqrt(lower * upper));
-        for (int i = 0; i < n; ++i) S.q[i] = -S.ghat[i];
+        __syncwarp();
+        int newton = 0;
         for (int it = 0; it < 10; ++it) {
+            ++newton;
             if (alpha < lower || alpha > upper) alpha = fmax(0.001 * upper, sqrt(lower * upper));
             int tries = 0;
-            while (!ba_tridiag_solve(S, n, alpha, true, S.q, S.yhat) && tries < 64) {     // rounding: T + alpha I not positive
+            while (!ba_pcr_solve(S, n, alpha, S.q, S.yhat, lane) && tries < 64) {        // rounding: T + alpha I not positive
                 const double floor_a = 2.220446049250313e-16 * ctl->a_diag * (double)(1 << (tries < 30 ? tries : 30));
                 lower = fmax(lower, alpha);
                 alpha = fmax(2.0 * alpha, floor_a);
                 if (alpha > upper) upper = alpha;
                 ++tries;
             }
-            ba_tridiag_solve(S, n, alpha, false, S.yhat, S.zhat);
-            const double pn = ba_norm2_serial(S.yhat, n);
-            double yz = 0.0;
-            for (int i = 0; i < n; ++i) yz += S.yhat[i] * S.zhat[i];
+            ba_pcr_solve(S, n, alpha, S.yhat, S.zhat, lane);
+            double p2 = 0.0, yz = 0.0;
+            for (int i = lane; i < n; i += 32) { p2 += S.yhat[i] * S.yhat[i]; yz += S.yhat[i] * S.zhat[i]; }
+            const double pn = sqrt(ba_warp_sum(p2));
+            yz = ba_warp_sum(yz);
             const double phi = pn - Delta, phi_prime = -yz / pn;
             if (phi < 0) upper = alpha;
             const double ratio = phi / phi_prime;
@@ -944,25 +995,30 @@ BA_DEV void ba_solve_tr(const BAShared& S, int n) {
             if (fabs(phi) < 0.01 * Delta) break;
         }
         int tries = 0;
-        while (!ba_tridiag_solve(S, n, alpha, true, S.q, S.yhat) && tries < 64) {
+        while (!ba_pcr_solve(S, n, alpha, S.q, S.yhat, lane) && tries < 64) {
             alpha = fmax(2.0 * alpha, 2.220446049250313e-16 * ctl->a_diag * (double)(1 << (tries < 30 ? tries : 30)));
             ++tries;
         }
-        const double pn = ba_norm2_serial(S.yhat, n);
+        double p2 = 0.0;
+        for (int i = lane; i < n; i += 32) p2 += S.yhat[i] * S.yhat[i];
+        const double pn = sqrt(ba_warp_sum(p2));
         const double sc = pn > 0.0 ? Delta / pn : 0.0;
-        double qd = 0.0, l = 0.0;                                   // p^T A p = phat^T T phat
-        for (int i = 0; i < n; ++i) {
-            S.yhat[i] *= sc;
+        for (int i = lane; i < n; i += 32) S.yhat[i] *= sc;
+        __syncwarp();
+        double l = 0.0, qd = 0.0;                                   // g^T p = ghat^T phat, p^T A p = phat^T T phat
+        for (int i = lane; i < n; i += 32) {
             l += S.yhat[i] * S.ghat[i];
-        }
-        for (int i = 0; i < n; ++i) {
             double r = S.td[i] * S.yhat[i];
             if (i > 0) r += S.te[i - 1] * S.yhat[i - 1];
             if (i + 1 < n) r += S.te[i] * S.yhat[i + 1];
             qd += S.yhat[i] * r;
         }
-        ctl->pred = -(0.5 * qd + l);
-        ctl->alpha = alpha;
+        l = ba_warp_sum(l); qd = ba_warp_sum(qd);
+        if (lane == 0) {
+            ctl->pred = -(0.5 * qd + l);
+            ctl->alpha = alpha;
+            ctl->tr_calls += 1; ctl->tr_its += newton;
+        }
     }
     __syncthreads();
     for (int r = tid; r < n; r += nt) {                            // p = Q phat
@@ -1010,11 +1066,11 @@ BA_DEV void ba_solve_body(const BAParams& P, unsigned char* smem) {
     // reference objective and DLT points at the start
     double v3[3], tot[3];
     ba_cost_pass(P, S, S.Rt, true, scratch, v3);
-    ba_grid_sum3(P, slot, v3, tot); slot ^= 1;
+    ba_grid_sum3(P, S, slot, v3, tot); slot ^= 1;
     if (tid == 0) {
         ctl->cost_initial = tot[0]; ctl->cost = tot[0]; ctl->finite = tot[1] == 0.0; ctl->n_valid = (int)tot[2];
         ctl->pf_cost0 = 0.0; ctl->pf_cost1 = 0.0; ctl->pf_it = 0;
-        ctl->nfev = 0; ctl->njev = 0; ctl->iteration = 0; ctl->termination = -99; ctl->g_norm = 0.0;
+        ctl->nfev = 0; ctl->njev = 0; ctl->iteration = 0; ctl->termination = -99; ctl->g_norm = 0.0; ctl->tr_its = 0; ctl->tr_calls = 0;
     }
     __syncthreads();
     if (ctl->n_valid == 0) {
@@ -1022,6 +1078,7 @@ BA_DEV void ba_solve_body(const BAParams& P, unsigned char* smem) {
             mocap_ba_report r;
             r.cost_initial = 0; r.cost_final = 0; r.optimality = 0; r.n_iterations = 0; r.n_fev = 0; r.status = -3; r.n_residuals = 0;
             r.prefit_cost_initial = 0; r.prefit_cost_final = 0; r.prefit_iterations = 0; r.n_launches = 1;
+            r.n_tr_solves = 0; r.n_tr_newton = 0;
             for (int k = 0; k < 8; ++k) r.phase_ms[k] = 0.0f;
             *P.report = r;
         }
@@ -1084,7 +1141,7 @@ BA_DEV void ba_solve_body(const BAParams& P, unsigned char* smem) {
             __syncthreads();
             BA_TICK(BA_PH_PF_SOLVE);
             v3[0] = ba_prefit_backsub(P, S, lambda, scratch); v3[1] = 0.0; v3[2] = 0.0;
-            ba_grid_sum3(P, slot, v3, tot); slot ^= 1;
+            ba_grid_sum3(P, S, slot, v3, tot); slot ^= 1;
             BA_TICK(BA_PH_PF_TRIAL);
             const double cost = ctl->pcost, cost_new = tot[0];
             const bool accept = cost_new < cost && isfinite(cost_new);
@@ -1170,7 +1227,7 @@ BA_DEV void ba_solve_body(const BAParams& P, unsigned char* smem) {
             for (int c = tid; c < C; c += nt) ba_pose_from_x(S.x_new, c, S.Rt_new + 12 * c);
             __syncthreads();
             ba_cost_pass(P, S, S.Rt_new, false, scratch, v3);
-            ba_grid_sum3(P, slot, v3, tot); slot ^= 1;
+            ba_grid_sum3(P, S, slot, v3, tot); slot ^= 1;
             BA_TICK(BA_PH_TRIAL);
             if (tid == 0) {
                 ctl->nfev += 1;
@@ -1238,7 +1295,7 @@ BA_DEV void ba_solve_body(const BAParams& P, unsigned char* smem) {
             r.cost_initial = ctl->cost_initial; r.cost_final = ctl->cost; r.optimality = ctl->g_norm;
             r.n_iterations = ctl->iteration; r.n_fev = ctl->nfev; r.status = ctl->termination; r.n_residuals = ctl->n_valid;
             r.prefit_cost_initial = ctl->pf_cost0; r.prefit_cost_final = ctl->pf_cost1; r.prefit_iterations = ctl->pf_it;
-            r.n_launches = 1;
+            r.n_launches = 1; r.n_tr_solves = ctl->tr_calls; r.n_tr_newton = ctl->tr_its;
             const unsigned long long t_end = ba_clock();
             ctl->prof[BA_PH_SETUP] += t_end - ctl->t_last;
             for (int k = 0; k < 8; ++k) r.phase_ms[k] = (float)((double)ctl->prof[k] * 1e-6);

@@ -67,6 +67,7 @@ struct mocap_ctx {
     void*     d_scratch; size_t scratch_bytes;
     // S4 on the device (ba_dev.cu): workspace of k_ba_solve, launch shape
     void*     d_ba_ws; size_t ba_ws_bytes; int ba_threads; int ba_grid; size_t ba_smem;
+    unsigned* d_match_counter; int match_ctas_per_sm;   // k_match_triangulate: frame-set claim counter, resident CTAs per SM
     const int32_t* img_flags_cur;   // set by the pipelines: the matcher folds the images' S1 flags into the frame-set's
     int32_t*  track_xy_cur;   // set for the duration of mocap_pipeline_tracks_dev: where the matcher leaves the winners' pixels
     // capture-side preprocessing

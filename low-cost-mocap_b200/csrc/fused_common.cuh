@@ -65,7 +65,10 @@ __device__ __forceinline__ void finish_image(const FusedParams& P, unsigned char
     __threadfence();                                   // release: blob list of this image
     __syncwarp();
     unsigned sd = 0;
-    if (lane == 0) sd = atomicAdd(&P.set_done[set], 1u);
+    if (lane == 0) {
+        __threadfence();                               // publishing lane: fence after the warp barrier, then the counter
+        sd = atomicAdd(&P.set_done[set], 1u);
+    }
     sd = __shfl_sync(0xffffffffu, sd, 0);
     if (sd != (unsigned)P.C - 1) return;
 

@@ -65,7 +65,10 @@ k_pipeline_fused(const FusedParams P) {
         __threadfence();                                   // release: this warp's list entries
         __syncwarp();
         unsigned done = 0;
-        if (lane == 0) done = atomicAdd(&P.img_done[img], 1u);
+        if (lane == 0) {
+            __threadfence();                               // the publishing lane's fence comes AFTER the warp barrier: the other
+            done = atomicAdd(&P.img_done[img], 1u);        // lanes' writes are then ordered before the counter (PTX memory model)
+        }
         done = __shfl_sync(0xffffffffu, done, 0);
         if (done != (unsigned)P.units_per_image - 1) continue;
 

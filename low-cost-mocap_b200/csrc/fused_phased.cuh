@@ -80,7 +80,10 @@ __device__ __forceinline__ int phased_reduce_image(const FusedParams& P, unsigne
     __threadfence();                                   // release: blob list of this image
     __syncwarp();
     unsigned sd = 0;
-    if (lane == 0) sd = atomicAdd(&P.set_done[set], 1u);
+    if (lane == 0) {
+        __threadfence();                               // publishing lane: fence after the warp barrier
+        sd = atomicAdd(&P.set_done[set], 1u);
+    }
     sd = __shfl_sync(0xffffffffu, sd, 0);
     if (sd != (unsigned)P.C - 1) return -1;
     __threadfence();                                   // acquire: blob lists of the other cameras
@@ -159,6 +162,7 @@ k_pipeline_phased(const FusedParams P) {
             __threadfence();                               // release: this warp's list entries
             __syncwarp();
             if (lane == 0) {
+                __threadfence();                           // publishing lane: fence after the warp barrier
                 const unsigned done = atomicAdd(&P.img_done[img], 1u);
                 if (done == (unsigned)P.units_per_image - 1) q.img[atomicAdd(&q.n_img, 1u)] = (uint32_t)img;
             }

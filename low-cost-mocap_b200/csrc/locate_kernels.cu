@@ -5,7 +5,9 @@
 // cartesian-product order, for the first ordered pair (a, b) of those neighbours that is 0.15 +- 0.025
 // apart; the object sits midway between a and b, heads along a - b (folded into [-pi/2, pi/2], sign
 // flipped), its error is the mean of the three reprojection errors and its droneIndex comes from the
-// side of the axis point i lies on.  Only i is marked as used (the reference never checks a, b).
+// side of the axis point i lies on.  i, a and b all go on the reference's already_matched_points list, but that list
+// only screens the OUTER index: a matched point is skipped as a later i, yet stays available as a / b of another
+// i (so up to one object per point can come out; the mirror sizes max_objects accordingly).
 // The greedy scan is order dependent, so one thread owns one frame-set and walks it sequentially;
 // frame-sets are independent.
 #include "common.cuh"

@@ -17,6 +17,9 @@
 #include "geom.cuh"
 #include "match_device.cuh"
 
+// (measured, round 2: __launch_bounds__(128, 5) = 96 registers / 20 warps per SM together with the claim counter
+// below is no faster than 128 registers / 16 warps -- 4.09 against 4.02 ms per 4000 heavy frame-sets -- so the
+// register budget stays at 128)
 __global__ void __launch_bounds__(128)
 k_match_triangulate(const CameraTables* __restrict__ tb, const int32_t* blob_xy, const int32_t* blob_n,
                     const uint32_t* __restrict__ set_list, uint32_t* set_count,
@@ -44,11 +47,19 @@ k_match_triangulate(const CameraTables* __restrict__ tb, const int32_t* blob_xy,
         }
         return;
     }
-    const int set = blockIdx.x * warps + wid;
-    if (set >= n_sets) return;
-    match_triangulate_warp(tb, ws, blob_xy + (size_t)set * C * MB * 2, blob_n + (size_t)set * C, set, lane,
-                           C, MB, RMAX, KC, GMAX, obj, err_out, n_obj, set_flags, chosen, track_xy,
-                           img_flags ? img_flags + (size_t)set * C : nullptr);
+    // persistent warps claim frame-sets from a counter: the work per frame-set varies by an order of magnitude (a few
+    // to hundreds of candidate groups), a static assignment leaves the SMs idle behind the heaviest CTAs
+    while (true) {
+        unsigned s = 0;
+        if (lane == 0) s = atomicAdd(set_count, 1u);
+        s = __shfl_sync(0xffffffffu, s, 0);
+        if (s >= (unsigned)n_sets) break;
+        const int set = (int)s;
+        match_triangulate_warp(tb, ws, blob_xy + (size_t)set * C * MB * 2, blob_n + (size_t)set * C, set, lane,
+                               C, MB, RMAX, KC, GMAX, obj, err_out, n_obj, set_flags, chosen, track_xy,
+                               img_flags ? img_flags + (size_t)set * C : nullptr);
+        __syncwarp();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -106,8 +117,10 @@ int launch_match(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n, 
     const mocap_config& c = ctx->cfg;
     const int warps = 4;
     const size_t smem = match_smem_bytes(c, warps);
-    const int grid = (n_sets + warps - 1) / warps;
-    k_match_triangulate<<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_tables, blob_xy, blob_n, nullptr, nullptr, n_sets, c.n_cam,
+    int grid = (n_sets + warps - 1) / warps;
+    if (grid > ctx->num_sms * ctx->match_ctas_per_sm) grid = ctx->num_sms * ctx->match_ctas_per_sm;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_match_counter, 0, sizeof(unsigned), ctx->stream));
+    k_match_triangulate<<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_tables, blob_xy, blob_n, nullptr, ctx->d_match_counter, n_sets, c.n_cam,
                                                                  c.max_blobs, c.max_roots, c.max_cands,
                                                                  (uint32_t)c.max_groups, obj, err, n_obj, set_flags, chosen, ctx->track_xy_cur, ctx->img_flags_cur);
     CUDA_TRY(ctx, cudaGetLastError());
@@ -145,5 +158,9 @@ int match_kernels_init(mocap_ctx* ctx) {
     const size_t smem = match_smem_bytes(ctx->cfg, 4);
     if (smem > 200 * 1024) return mocap_fail(ctx, MOCAP_EINVAL, "matcher state needs %zu bytes of shared memory per CTA; lower max_roots/max_cands", smem);
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_match_triangulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match_triangulate, 128, smem));
+    ctx->match_ctas_per_sm = per_sm > 0 ? per_sm : 1;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_match_counter, sizeof(unsigned)));
     return MOCAP_OK;
 }

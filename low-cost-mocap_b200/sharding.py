@@ -97,7 +97,11 @@ class TrackBuffer:
 
         With ``async_op=True`` returns ``(views, work)``: the collective is only enqueued (after the work
         already on the current stream), so the next batch's kernels can run while the tracks travel; call
-        ``work.wait()`` before reading the views or writing this buffer again (use two buffers in turn)."""
+        ``work.wait()`` before reading the views or writing this buffer again (use two buffers in turn).
+
+        Every rank must hold a buffer of the SAME size (``all_gather_into_tensor``): size the buffers for
+        ``ceil(n_total / world)`` frame-sets on every rank and ignore the padding frame-sets of the short shards
+        (their ``n`` stays 0); ``all_gather_tracks`` above does that padding itself for ragged totals."""
         import torch
         import torch.distributed as dist
         world = dist.get_world_size(group)

@@ -37,5 +37,6 @@ extern "C" int hc_ba_solve_dev(const double* obs, const uint8_t* mask, int m, in
     report[0] = rep.cost_initial; report[1] = rep.cost_final; report[2] = rep.optimality; report[3] = rep.n_iterations;
     report[4] = rep.n_fev; report[5] = rep.status; report[6] = rep.n_residuals; report[7] = rep.prefit_cost_initial;
     report[8] = rep.prefit_cost_final; report[9] = rep.prefit_iterations; report[10] = (double)smem;
+    report[11] = rep.n_tr_solves; report[12] = rep.n_tr_newton;
     return 0;
 }

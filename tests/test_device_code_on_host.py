@@ -479,10 +479,10 @@ def ba_emu():
         C = mask.shape[1]
         obs = np.ascontiguousarray(obs, np.float64); mask = np.ascontiguousarray(mask, np.uint8)
         Ks = np.ascontiguousarray(np.stack([K] * C)); R = np.ascontiguousarray(R.copy()); t = np.ascontiguousarray(t.copy())
-        rep = np.zeros(11)
+        rep = np.zeros(13)
         assert emu.hc_ba_solve_dev(p(obs), p(mask), obs.shape[0], C, p(Ks), p(R), p(t), 1e-2, max_nfev, jac_mode, int(prefit), 50, n_ctas, n_threads, p(rep)) == 0
         keys = ["cost_initial", "cost_final", "optimality", "n_iterations", "n_fev", "status", "n_residuals", "prefit_cost_initial",
-                "prefit_cost_final", "prefit_iterations", "smem"]
+                "prefit_cost_final", "prefit_iterations", "smem", "n_tr_solves", "n_tr_newton"]
         return R, t, dict(zip(keys, rep))
 
     def model_solve(obs, mask, K, R, t, jac_mode=1):

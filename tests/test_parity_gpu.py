@@ -22,7 +22,8 @@ ERR_RTOL = 1e-9       # reprojection errors are float32-quantised upstream; expe
 @pytest.fixture(scope="module")
 def torch():
     import torch
-    assert torch.cuda.is_available(), "these tests need the B200"
+    if not torch.cuda.is_available():
+        pytest.skip("needs the B200 (run with -m gpu on the GPU box)")
     return torch
 
 
