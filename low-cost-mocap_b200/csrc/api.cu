@@ -195,7 +195,8 @@ int mocap_set_world_transform(mocap_ctx* ctx, const double* M) {
 // (written by the last CTA of the blob fallback kernel): no synchronisation, a stale or torn value only steers
 // this heuristic, both pipelines give the same results.
 static bool pick_fused(const mocap_ctx* ctx, int channels) {
-    if (!ctx->use_fused || channels != 1) return false;
+    if (!ctx->use_fused) return false;
+    if (channels != 1 && (ctx->use_tma || ctx->use_phased)) return false;     // the experimental variants stream 1-channel frames only
     if (!ctx->pipeline_auto) return true;
     const unsigned long long blobs = ctx->h_stat[0], images = ctx->h_stat[1];
     if (images == 0) return true;
@@ -293,8 +294,12 @@ int mocap_pipeline_tracks_dev(mocap_ctx* ctx, const uint8_t* frames, int n_frame
         // the launchers hand this to the matcher (frame-set indices inside a launch group start at 0)
         ctx->track_xy_cur = track_xy ? track_xy + (size_t)s0 * ctx->cfg.max_roots * C * 2 : nullptr;
         if (fused) {
-            st = (ctx->use_tma ? launch_pipeline_tma : launch_pipeline_fused)(ctx, frames + (size_t)s0 * set_bytes, ns, threshold, obj + (size_t)s0 * ctx->cfg.max_roots * 3,
-                                       err + (size_t)s0 * ctx->cfg.max_roots, n_obj + s0, set_flags ? set_flags + s0 : nullptr);
+            if (ctx->use_tma)
+                st = launch_pipeline_tma(ctx, frames + (size_t)s0 * set_bytes, ns, threshold, obj + (size_t)s0 * ctx->cfg.max_roots * 3,
+                                         err + (size_t)s0 * ctx->cfg.max_roots, n_obj + s0, set_flags ? set_flags + s0 : nullptr);
+            else
+                st = launch_pipeline_fused(ctx, frames + (size_t)s0 * set_bytes, ns, threshold, obj + (size_t)s0 * ctx->cfg.max_roots * 3,
+                                           err + (size_t)s0 * ctx->cfg.max_roots, n_obj + s0, set_flags ? set_flags + s0 : nullptr, channels);
             if (st) break;
             continue;
         }
@@ -351,8 +356,12 @@ int mocap_pipeline_host(mocap_ctx* ctx, const uint8_t* frames, int n_frame_sets,
         CUDA_TRY(ctx, cudaEventRecord(copied[k], cs));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, copied[k], 0));
         if (fused) {
-            st = (ctx->use_tma ? launch_pipeline_tma : launch_pipeline_fused)(ctx, ctx->d_stage[k], ns, threshold, ctx->d_obj + (size_t)s0 * RM * 3, ctx->d_err + (size_t)s0 * RM,
-                                       ctx->d_nobj + s0, ctx->d_setflags + s0);
+            if (ctx->use_tma)
+                st = launch_pipeline_tma(ctx, ctx->d_stage[k], ns, threshold, ctx->d_obj + (size_t)s0 * RM * 3, ctx->d_err + (size_t)s0 * RM,
+                                         ctx->d_nobj + s0, ctx->d_setflags + s0);
+            else
+                st = launch_pipeline_fused(ctx, ctx->d_stage[k], ns, threshold, ctx->d_obj + (size_t)s0 * RM * 3, ctx->d_err + (size_t)s0 * RM,
+                                           ctx->d_nobj + s0, ctx->d_setflags + s0, channels);
             if (st) break;
             CUDA_TRY(ctx, cudaEventRecord(ctx->stage_free[k], ctx->stream));
             continue;

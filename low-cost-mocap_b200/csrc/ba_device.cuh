@@ -311,7 +311,7 @@ struct BAShared {
     double* colRt; int* colcam; double* dx;   // [n][12], [n], [n]
     double* g; double* p; double* q; double* w;   // [n]
     double* td; double* te; double* ghat; double* yhat; double* zhat; double* hv; double* hp; double* hu;   // [n] tridiagonal form of A
-    double* pcr;                       // [8][n] cyclic-reduction work arrays (two generations of a, b, c, d)
+    double* pcr;                       // [10][n] cyclic-reduction work arrays (two generations of a, b, 1/b, c, d)
     uint8_t* pi; uint8_t* pj;          // [npair] pair -> (i, j), i <= j
     double* acc;                       // [pstride] this CTA's partial system
     double* scratch;                   // [threads] block sums
@@ -343,7 +343,7 @@ static __host__ __device__ inline size_t ba_smem_bytes(int C, int nt) {
     b += ba_align16((size_t)2 * C * 12 * 8);
     b += ba_align16((size_t)n * 12 * 8) + ba_align16((size_t)n * 4) + ba_align16((size_t)n * 8);
     b += 12 * ba_align16((size_t)n * 8);
-    b += ba_align16((size_t)8 * n * 8);
+    b += ba_align16((size_t)10 * n * 8);
     b += 2 * ba_align16((size_t)npair);
     b += ba_align16((size_t)pstride * 8);
     b += ba_align16((size_t)nt * 8);
@@ -374,7 +374,7 @@ BA_DEV BAShared ba_carve(unsigned char* raw, int C, int nt) {
     s.hv = reinterpret_cast<double*>(raw); raw += ba_align16((size_t)n * 8);
     s.hp = reinterpret_cast<double*>(raw); raw += ba_align16((size_t)n * 8);
     s.hu = reinterpret_cast<double*>(raw); raw += ba_align16((size_t)n * 8);
-    s.pcr = reinterpret_cast<double*>(raw); raw += ba_align16((size_t)8 * n * 8);
+    s.pcr = reinterpret_cast<double*>(raw); raw += ba_align16((size_t)10 * n * 8);
     s.pi = raw; raw += ba_align16((size_t)npair);
     s.pj = raw; raw += ba_align16((size_t)npair);
     s.acc = reinterpret_cast<double*>(raw); raw += ba_align16((size_t)pstride * 8);
@@ -915,37 +915,41 @@ BA_DEV double ba_warp_sum(double v) {
 // twice per Newton step on alpha and used to spend most of its time in that chain.  For a positive definite matrix
 // every diagonal entry stays positive (they are Schur complements); returns false (warp-uniform) if one does not.
 BA_DEV bool ba_pcr_solve(const BAShared& S, int n, double alpha, const double* rhs, double* x, int lane) {
+    // two generations of (a, b, 1/b, c, d): an equation stores the reciprocal of its diagonal entry next to it, so that
+    // a step costs ONE division per equation (its own new diagonal) and its neighbours only multiply
     double* buf = S.pcr;
     int cur = 0;
+    bool ok = true;
     for (int i = lane; i < n; i += 32) {
+        const double b = S.td[i] + alpha;
+        if (!(b > 0.0)) ok = false;
         buf[0 * n + i] = i > 0 ? S.te[i - 1] : 0.0;               // a: sub-diagonal
-        buf[1 * n + i] = S.td[i] + alpha;                          // b: diagonal
-        buf[2 * n + i] = i + 1 < n ? S.te[i] : 0.0;                // c: super-diagonal
-        buf[3 * n + i] = rhs[i];
+        buf[1 * n + i] = b;                                        // diagonal
+        buf[2 * n + i] = 1.0 / b;
+        buf[3 * n + i] = i + 1 < n ? S.te[i] : 0.0;                // c: super-diagonal
+        buf[4 * n + i] = rhs[i];
     }
     __syncwarp();
-    bool ok = true;
     for (int st = 1; st < n; st <<= 1) {
-        const double* A0 = buf + (size_t)(4 * cur + 0) * n; const double* B0 = buf + (size_t)(4 * cur + 1) * n;
-        const double* C0 = buf + (size_t)(4 * cur + 2) * n; const double* D0 = buf + (size_t)(4 * cur + 3) * n;
-        double* A1 = buf + (size_t)(4 * (cur ^ 1) + 0) * n; double* B1 = buf + (size_t)(4 * (cur ^ 1) + 1) * n;
-        double* C1 = buf + (size_t)(4 * (cur ^ 1) + 2) * n; double* D1 = buf + (size_t)(4 * (cur ^ 1) + 3) * n;
+        const double* A0 = buf + (size_t)(5 * cur + 0) * n; const double* B0 = buf + (size_t)(5 * cur + 1) * n;
+        const double* R0 = buf + (size_t)(5 * cur + 2) * n; const double* C0 = buf + (size_t)(5 * cur + 3) * n;
+        const double* D0 = buf + (size_t)(5 * cur + 4) * n;
+        double* A1 = buf + (size_t)(5 * (cur ^ 1) + 0) * n; double* B1 = buf + (size_t)(5 * (cur ^ 1) + 1) * n;
+        double* R1 = buf + (size_t)(5 * (cur ^ 1) + 2) * n; double* C1 = buf + (size_t)(5 * (cur ^ 1) + 3) * n;
+        double* D1 = buf + (size_t)(5 * (cur ^ 1) + 4) * n;
         for (int i = lane; i < n; i += 32) {
             const int im = i - st, ip = i + st;
             double bb = B0[i], dd = D0[i], aa = 0.0, cc = 0.0;
+            if (im >= 0) { const double k1 = A0[i] * R0[im]; bb -= C0[im] * k1; dd -= D0[im] * k1; aa = -A0[im] * k1; }
+            if (ip < n) { const double k2 = C0[i] * R0[ip]; bb -= A0[ip] * k2; dd -= D0[ip] * k2; cc = -C0[ip] * k2; }
             if (!(bb > 0.0)) ok = false;
-            if (im >= 0) { const double k1 = A0[i] / B0[im]; bb -= C0[im] * k1; dd -= D0[im] * k1; aa = -A0[im] * k1; }
-            if (ip < n) { const double k2 = C0[i] / B0[ip]; bb -= A0[ip] * k2; dd -= D0[ip] * k2; cc = -C0[ip] * k2; }
-            A1[i] = aa; B1[i] = bb; C1[i] = cc; D1[i] = dd;
+            A1[i] = aa; B1[i] = bb; R1[i] = 1.0 / bb; C1[i] = cc; D1[i] = dd;
         }
         __syncwarp();
         cur ^= 1;
     }
-    const double* Bf = buf + (size_t)(4 * cur + 1) * n; const double* Df = buf + (size_t)(4 * cur + 3) * n;
-    for (int i = lane; i < n; i += 32) {
-        if (!(Bf[i] > 0.0)) ok = false;
-        x[i] = Df[i] / Bf[i];
-    }
+    const double* Rf = buf + (size_t)(5 * cur + 2) * n; const double* Df = buf + (size_t)(5 * cur + 4) * n;
+    for (int i = lane; i < n; i += 32) x[i] = Df[i] * Rf[i];
     ok = __ballot_sync(0xffffffffu, ok ? 0 : 1) == 0u;
     __syncwarp();
     return ok;

@@ -110,5 +110,5 @@ int launch_match_list(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blo
 int launch_pipeline_tma(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int threshold,
                         double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
 int launch_pipeline_fused(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int threshold,
-                          double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
+                          double* obj, double* err, int32_t* n_obj, int32_t* set_flags, int channels = 1);
 int timing_flush(mocap_ctx* ctx);

@@ -10,6 +10,8 @@ struct FusedParams {
     long long total_units;
     int n_sets, C, W, H;
     int seg_per_image, units_per_image, iters_per_unit;
+    int u4_per_image;              // 128-bit words per image: seg_per_image (1 channel) or 3 * seg_per_image (H x W x 3 interleaved)
+    int threshold;                 // the raw threshold (the 3-channel path compares the grey value with it)
     ThreshConst tc;
     int E;                         // stride of the global segment lists
     uint32_t* seg_count; uint32_t* seg_list;

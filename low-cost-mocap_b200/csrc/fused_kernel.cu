@@ -23,7 +23,7 @@ size_t fused_slab_bytes(const mocap_config& c) {
 }
 
 int launch_pipeline_fused(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int threshold,
-                          double* obj, double* err, int32_t* n_obj, int32_t* set_flags) {
+                          double* obj, double* err, int32_t* n_obj, int32_t* set_flags, int channels) {
     if (n_sets <= 0) return MOCAP_OK;
     const mocap_config& c = ctx->cfg;
     FusedParams P;
@@ -31,7 +31,9 @@ int launch_pipeline_fused(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int
     P.frames = reinterpret_cast<const uint4*>(frames);
     P.n_sets = n_sets; P.C = c.n_cam; P.W = c.width; P.H = c.height;
     P.seg_per_image = c.width * c.height / MOCAP_SEG_PX;
-    const int iters_total = (P.seg_per_image + FUSED_SEGS_PER_ITER - 1) / FUSED_SEGS_PER_ITER;
+    P.u4_per_image = P.seg_per_image * (channels == 3 ? 3 : 1);
+    P.threshold = threshold;
+    const int iters_total = (P.u4_per_image + FUSED_SEGS_PER_ITER - 1) / FUSED_SEGS_PER_ITER;
     P.units_per_image = (iters_total + 15) / 16;             // ~16 iterations (64 KB) per unit
     P.iters_per_unit = (iters_total + P.units_per_image - 1) / P.units_per_image;
     P.total_units = (long long)n_sets * c.n_cam * P.units_per_image;
@@ -72,6 +74,14 @@ int launch_pipeline_fused(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int
             if (P.tc.use_and) k_pipeline_phased<false, true><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
             else k_pipeline_phased<false, false><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
         }
+    } else if (channels == 3) {                             // H x W x 3 interleaved: the layout _find_dot receives
+        if (wide) {
+            if (P.tc.use_and) k_pipeline_fused<true, true, true><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
+            else k_pipeline_fused<true, false, true><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
+        } else {
+            if (P.tc.use_and) k_pipeline_fused<false, true, true><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
+            else k_pipeline_fused<false, false, true><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
+        }
     } else if (wide) {
         if (P.tc.use_and) k_pipeline_fused<true, true><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
         else k_pipeline_fused<true, false><<<grid, FUSED_WARPS * 32, smem, ctx->stream>>>(P);
@@ -102,6 +112,10 @@ int fused_kernel_init(mocap_ctx* ctx) {
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pipeline_fused<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;      // persistent grid = what is actually co-resident
     if (ctx->use_phased) {
         const int psmem = (int)(smem + sizeof(PhasedQueues));

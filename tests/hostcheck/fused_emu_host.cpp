@@ -18,7 +18,7 @@ alignas(16) unsigned char smem_raw[64 * 1024 * 4];            // the kernel's `e
 extern "C" int hc_pipeline_fused(const uint8_t* frames, int n_sets, int C, int W, int H, int threshold, const double* K, const double* R,
                                  const double* t, int MB, int E, int RMAX, int KC, unsigned GMAX, int n_warps, int runs, int phased,
                                  double* obj, double* err, int32_t* n_obj, int32_t* set_flags, int32_t* blob_xy, int32_t* blob_n,
-                                 uint32_t* img_worklist, uint32_t* set_worklist, long long* counters) {
+                                 uint32_t* img_worklist, uint32_t* set_worklist, long long* counters, int channels) {
     static CameraTables T;
     memset(&T, 0, sizeof(T));
     build_camera_tables(T, C, K, R, t);
@@ -28,7 +28,9 @@ extern "C" int hc_pipeline_fused(const uint8_t* frames, int n_sets, int C, int W
     P.frames = reinterpret_cast<const uint4*>(frames);
     P.n_sets = n_sets; P.C = C; P.W = W; P.H = H;
     P.seg_per_image = W * H / MOCAP_SEG_PX;
-    const int iters_total = (P.seg_per_image + FUSED_SEGS_PER_ITER - 1) / FUSED_SEGS_PER_ITER;
+    P.u4_per_image = P.seg_per_image * (channels == 3 ? 3 : 1);
+    P.threshold = threshold;
+    const int iters_total = (P.u4_per_image + FUSED_SEGS_PER_ITER - 1) / FUSED_SEGS_PER_ITER;
     P.units_per_image = (iters_total + 15) / 16;
     P.iters_per_unit = (iters_total + P.units_per_image - 1) / P.units_per_image;
     P.total_units = (long long)n_sets * C * P.units_per_image;
@@ -66,6 +68,9 @@ extern "C" int hc_pipeline_fused(const uint8_t* frames, int n_sets, int C, int W
             if (phased) {
                 if (wide) { if (P.tc.use_and) k_pipeline_phased<true, true>(P); else k_pipeline_phased<true, false>(P); }
                 else      { if (P.tc.use_and) k_pipeline_phased<false, true>(P); else k_pipeline_phased<false, false>(P); }
+            } else if (channels == 3) {
+                if (wide) { if (P.tc.use_and) k_pipeline_fused<true, true, true>(P); else k_pipeline_fused<true, false, true>(P); }
+                else      { if (P.tc.use_and) k_pipeline_fused<false, true, true>(P); else k_pipeline_fused<false, false, true>(P); }
             } else {
                 if (wide) { if (P.tc.use_and) k_pipeline_fused<true, true>(P); else k_pipeline_fused<true, false>(P); }
                 else      { if (P.tc.use_and) k_pipeline_fused<false, true>(P); else k_pipeline_fused<false, false>(P); }

@@ -218,7 +218,8 @@ def fused_emu():
 
     def run(frames, K, R, t, threshold=51, max_blobs=64, E=1024, max_roots=128, max_cands=8, max_groups=4096, n_warps=8, runs=2, phased=0):
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
-        B, C, H, W = frames.shape
+        channels = 3 if frames.ndim == 5 else 1                 # [B, C, H, W, 3]: the interleaved layout _find_dot receives
+        B, C, H, W = frames.shape[:4]
         K = np.ascontiguousarray(np.stack([K] * C) if np.ndim(K) == 2 else K, dtype=np.float64)
         R = np.ascontiguousarray(R, dtype=np.float64); t = np.ascontiguousarray(np.reshape(t, (C, 3)), dtype=np.float64)
         obj = np.zeros((B, max_roots, 3)); err = np.zeros((B, max_roots)); k = np.zeros(B, np.int32); fl = np.zeros(B, np.int32)
@@ -226,7 +227,7 @@ def fused_emu():
         iw = np.zeros(B * C, np.uint32); sw = np.zeros(B, np.uint32); cnt = np.zeros(4, np.int64)
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         rc = lib.hc_pipeline_fused(p(frames), B, C, W, H, int(threshold), p(K), p(R), p(t), max_blobs, E, max_roots, max_cands,
-                                   ctypes.c_uint(max_groups), n_warps, runs, phased, p(obj), p(err), p(k), p(fl), p(bxy), p(bn), p(iw), p(sw), p(cnt))
+                                   ctypes.c_uint(max_groups), n_warps, runs, phased, p(obj), p(err), p(k), p(fl), p(bxy), p(bn), p(iw), p(sw), p(cnt), channels)
         assert rc == 0
         return {"obj": obj, "err": err, "n": k, "flags": fl, "blob_xy": bxy.reshape(B, C, max_blobs, 2), "blob_n": bn.reshape(B, C),
                 "deferred_images": iw[:cnt[0]].tolist(), "deferred_sets": sw[:cnt[1]].tolist(), "dirty_scratch": int(cnt[2])}
@@ -566,3 +567,40 @@ def test_blob_device_code_flags_blobs_with_holes(blob_emu):
             assert bool(d["flags"] & 32) == has_hole, (trial, force_cta, d["flags"])
             assert d["flags"] & ~32 == 0
     assert seen[True] >= 15 and seen[False] >= 5
+
+
+def test_single_pass_kernel_on_host_three_channel_layout(fused_emu):
+    """The H x W x 3 interleaved layout (helpers.py:143-145) through the single-pass kernel: a 16-pixel segment is three
+    streamed words, the first word of a segment that passes the byte test computes the grey mask (cv2's 8-bit
+    RGB2GRAY), later words of the same segment stand down.  Checked against cv2 on coloured frames (blobs whose
+    brightest CHANNEL exceeds the threshold while the grey value does not, blobs across word and segment borders)."""
+    import cv2
+    rng = np.random.default_rng(8)
+    B, C, H, W = 3, 2, 48, 96
+    frames = rng.integers(0, 45, size=(B, C, H, W, 3), dtype=np.uint8)
+    for b in range(B):
+        for c in range(C):
+            for _ in range(6):
+                x, y = int(rng.integers(2, W - 8)), int(rng.integers(2, H - 6))
+                colour = rng.integers(30, 256, size=3)
+                if rng.integers(0, 3) == 0:
+                    colour = np.array([0, 0, 255]) if rng.integers(0, 2) else np.array([250, 20, 20])     # one bright channel only
+                frames[b, c, y:y + int(rng.integers(2, 5)), x:x + int(rng.integers(2, 7))] = colour
+    K = np.array([[60.0, 0, 48], [0, 60.0, 24], [0, 0, 1]])
+    R = np.stack([np.eye(3)] * C); t = np.array([[0.0, 0, 0], [-0.3, 0, 0]])
+    d = fused_emu(frames, K, R, t, n_warps=4, runs=2)
+    assert d["dirty_scratch"] == 0 and d["deferred_images"] == []
+    some = 0
+    for b in range(B):
+        for c in range(C):
+            grey = cv2.cvtColor(frames[b, c], cv2.COLOR_RGB2GRAY)
+            contours, _ = cv2.findContours((grey > 51).astype(np.uint8), cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+            ref = []
+            for cnt in contours:
+                m = cv2.moments(cnt)
+                if m["m00"] != 0:
+                    ref.append([int(m["m10"] / m["m00"]), int(m["m01"] / m["m00"])])
+            k = d["blob_n"][b, c]
+            assert k == len(ref) and np.array_equal(d["blob_xy"][b, c, :k], np.array(ref, np.int32).reshape(k, 2)), (b, c)
+            some += k
+    assert some >= 10
