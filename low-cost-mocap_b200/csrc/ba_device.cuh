@@ -245,25 +245,33 @@ BA_DEV bool ba_chol_factor(double* L, int n, int* flag) {
     __syncthreads();
     return true;
 }
+// The two triangular solves run in ONE warp (the other warps wait at a single barrier): a step is a handful of
+// multiply-adds per lane, and 2n CTA-wide barriers per solve cost ten times the arithmetic.
 BA_DEV void ba_solve_lower(const double* L, int n, double* v) {          // L y = v, in place
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int j = 0; j < n; ++j) {
-        __syncthreads();
-        if (tid == 0) v[j] /= L[j * n + j];
-        __syncthreads();
-        const double vj = v[j];
-        for (int i = j + 1 + tid; i < n; i += nt) v[i] -= L[i * n + j] * vj;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        for (int j = 0; j < n; ++j) {
+            const double vj = v[j] / L[j * n + j];                 // every lane the same value
+            __syncwarp();
+            if (lane == 0) v[j] = vj;
+            for (int i = j + 1 + lane; i < n; i += 32) v[i] -= L[i * n + j] * vj;
+            __syncwarp();
+        }
     }
     __syncthreads();
 }
 BA_DEV void ba_solve_upper(const double* L, int n, double* v) {          // L^T x = v, in place
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int j = n - 1; j >= 0; --j) {
-        __syncthreads();
-        if (tid == 0) v[j] /= L[j * n + j];
-        __syncthreads();
-        const double vj = v[j];
-        for (int i = tid; i < j; i += nt) v[i] -= L[j * n + i] * vj;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        for (int j = n - 1; j >= 0; --j) {
+            const double vj = v[j] / L[j * n + j];
+            __syncwarp();
+            if (lane == 0) v[j] = vj;
+            for (int i = lane; i < j; i += 32) v[i] -= L[j * n + i] * vj;
+            __syncwarp();
+        }
     }
     __syncthreads();
 }
@@ -461,21 +469,22 @@ BA_DEV void ba_reduce_system(const BAParams& P, const BAShared& S, int n_entries
     const int tid = threadIdx.x, nt = blockDim.x, G = gridDim.x, b = blockIdx.x;
     for (int e = tid; e < n_entries; e += nt) P.part[(size_t)b * P.pstride + e] = S.acc[e];
     ba_grid_sync(P.bar);
-    // every CTA adds its slice of the entries over all CTAs: 16 threads per entry fetch the partials side by side
-    // (the loads of one thread are independent), then one thread adds the 16 sub-sums in a fixed order
+    // every CTA adds its slice of the entries over all CTAs: W threads per entry fetch the partials side by side
+    // (the few loads of one thread are independent), then one thread adds the W sub-sums in a fixed order
     const int per = (n_entries + G - 1) / G;
     const int e0 = b * per, e1 = (e0 + per < n_entries) ? e0 + per : n_entries;
-    for (int base = e0; base < e1; base += nt / 16) {
-        const int e = base + tid / 16, j = tid & 15;
+    const int Wd = nt >= 64 * per ? 64 : 16;
+    for (int base = e0; base < e1; base += nt / Wd) {
+        const int e = base + tid / Wd, j = tid % Wd;
         double s = 0.0;
-        if (e < e1 && tid / 16 < nt / 16)
-            for (int g = j; g < G; g += 16) s += P.part[(size_t)g * P.pstride + e];
+        if (e < e1 && tid / Wd < nt / Wd)
+            for (int g = j; g < G; g += Wd) s += P.part[(size_t)g * P.pstride + e];
         __syncthreads();
         S.scratch[tid] = s;
         __syncthreads();
-        if (j == 0 && e < e1 && tid / 16 < nt / 16) {
+        if (j == 0 && e < e1 && tid / Wd < nt / Wd) {
             double t = 0.0;
-            for (int q = 0; q < 16; ++q) t += S.scratch[tid + q];
+            for (int q = 0; q < Wd; ++q) t += S.scratch[tid + q];
             P.fin[e] = t;
         }
     }

@@ -9,9 +9,18 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 synth = importlib.import_module("low-cost-mocap_b200.synth")
 
 
-def load_golden(name):
+def load_golden(name, n=None, frames=True):
+    """Golden vectors written by tests/golden/make_golden.py from the real reference.  ``n``: only the first n
+    frame-sets / frames (every per-frame-set array is cut; the deterministic clutter of a pixel depends on its flat
+    index only, so the first n frames get the same clutter as in the full set).  ``frames=False``: skip rebuilding
+    the frames (tests that start from the blob lists)."""
     z = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
-    if "frames_clean" in z:
+    if n is not None and "frames_clean" in z:
+        full = z["frames_clean"].shape[0]
+        for k, v in list(z.items()):
+            if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == full:
+                z[k] = v[:n]
+    if "frames_clean" in z and frames:
         z["frames"] = synth.add_clutter(z["frames_clean"], int(z["clutter_max"]), salt=int(z["clutter_salt"]))
     return z
 
