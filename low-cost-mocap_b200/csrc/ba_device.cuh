@@ -812,6 +812,13 @@ BA_DEV void ba_polish_accumulate(const BAParams& P, const BAShared& S) {
     __syncthreads();
 }
 
+// sum over the warp of per-lane partial sums, fixed tree: every CTA gets the same bits
+BA_DEV double ba_warp_sum(double v) {
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // load the reduced system P.fin -> S.A (full symmetric), S.g
 BA_DEV void ba_load_system(const BAParams& P, const BAShared& S, int n) {
     const int tid = threadIdx.x, nt = blockDim.x, npair = n * (n + 1) / 2;
@@ -844,9 +851,11 @@ BA_DEV void ba_tridiagonalise(const BAShared& S, int n) {
     for (int e = tid; e < n * n; e += nt) Qt[e] = (e / n == e % n) ? 1.0 : 0.0;
     __syncthreads();
     for (int k = 0; k + 2 < n; ++k) {
-        if (tid == 0) {
-            double sigma = 0.0;
-            for (int i = k + 1; i < n; ++i) sigma += A[(size_t)i * n + k] * A[(size_t)i * n + k];
+        if (tid < 32) {
+            double part = 0.0;
+            for (int i = k + 1 + tid; i < n; i += 32) part += A[(size_t)i * n + k] * A[(size_t)i * n + k];
+            const double sigma = ba_warp_sum(part);
+            if (tid == 0) {
             const double x0 = A[(size_t)(k + 1) * n + k];
             double tail = sigma - x0 * x0;                          // what the reflection has to remove
             if (!(tail > 0.0)) { ctl->hh_beta = 0.0; ctl->hh_alpha = x0; }
@@ -857,6 +866,7 @@ BA_DEV void ba_tridiagonalise(const BAShared& S, int n) {
                 ctl->hh_beta = 2.0 / (tail + v0 * v0);
                 ctl->hh_alpha = alpha;
                 S.hv[k + 1] = v0;
+            }
             }
         }
         __syncthreads();
@@ -880,10 +890,11 @@ BA_DEV void ba_tridiagonalise(const BAShared& S, int n) {
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            double dot = 0.0;
-            for (int i = k + 1; i < n; ++i) dot += S.hp[i] * S.hv[i];
-            ctl->hh_K = 0.5 * beta * dot;
+        if (tid < 32) {
+            double part = 0.0;
+            for (int i = k + 1 + tid; i < n; i += 32) part += S.hp[i] * S.hv[i];
+            const double dot = ba_warp_sum(part);
+            if (tid == 0) ctl->hh_K = 0.5 * beta * dot;
         }
         __syncthreads();
         const double K = ctl->hh_K;
@@ -909,13 +920,6 @@ BA_DEV void ba_tridiagonalise(const BAShared& S, int n) {
         S.ghat[j] = acc;
     }
     __syncthreads();
-}
-
-// sum over the warp of per-lane partial sums, fixed tree: every CTA gets the same bits
-BA_DEV double ba_warp_sum(double v) {
-#pragma unroll 1
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
 }
 
 // one WARP: (T + alpha I) x = rhs for the symmetric tridiagonal T = tridiag(S.td, S.te) by parallel cyclic reduction:

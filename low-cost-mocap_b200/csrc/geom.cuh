@@ -162,25 +162,41 @@ GEOM_HD void sym4_null_vector(const Sym4& B, double out[4]) {
 // The two agree to ~1e-13 relative.
 struct Ldl4 { double l10, l20, l30, l21, l31, l32, i0, i1, i2, i3; };
 
+// 1 / d for the pivots of the ITERATIVE solver below: the hardware's approximate reciprocal refined by two Newton steps
+// (full double precision to an ulp or two, a handful of instructions) instead of the correctly rounded division
+// (~40 instructions) -- the iteration converges to the same vector either way and its result is checked.  Everything
+// whose rounding the reference fixes (A entries, projections, the final dehomogenisation) keeps exact division.
+GEOM_HD double geom_rcp(double d) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(r, fma(-d, r, 1.0), r);
+    r = fma(r, fma(-d, r, 1.0), r);
+    return r;
+#else
+    return 1.0 / d;
+#endif
+}
+
 // LDL^T of B - shift I without pivoting; false on a zero / non-finite pivot.  n_neg = number of negative pivots.
 GEOM_HD bool sym4_ldl(const Sym4& B, double shift, Ldl4& f, int& n_neg) {
     const double b00 = B.v[0] - shift, b01 = B.v[1], b02 = B.v[2], b03 = B.v[3], b11 = B.v[4] - shift, b12 = B.v[5], b13 = B.v[6];
     const double b22 = B.v[7] - shift, b23 = B.v[8], b33 = B.v[9] - shift;
     if (!(b00 != 0.0)) return false;
-    f.i0 = 1.0 / b00;
+    f.i0 = geom_rcp(b00);
     f.l10 = b01 * f.i0; f.l20 = b02 * f.i0; f.l30 = b03 * f.i0;
     const double d1 = b11 - f.l10 * b01;
     if (!(d1 != 0.0)) return false;
-    f.i1 = 1.0 / d1;
+    f.i1 = geom_rcp(d1);
     f.l21 = (b12 - f.l20 * b01) * f.i1; f.l31 = (b13 - f.l30 * b01) * f.i1;
     const double d2 = b22 - f.l20 * b02 - f.l21 * (f.l21 * d1);
     if (!(d2 != 0.0)) return false;
-    f.i2 = 1.0 / d2;
+    f.i2 = geom_rcp(d2);
     f.l32 = (b23 - f.l30 * b02 - f.l31 * (f.l21 * d1)) * f.i2;
     double d3 = b33 - f.l30 * b03 - f.l31 * (f.l31 * d1) - f.l32 * (f.l32 * d2);
     if (!(d3 == d3)) return false;
     if (fabs(d3) < 1e-290) d3 = 1e-290;                 // exactly singular: any huge amplification along the null vector will do
-    f.i3 = 1.0 / d3;
+    f.i3 = geom_rcp(d3);
     n_neg = (b00 < 0.0) + (d1 < 0.0) + (d2 < 0.0) + (d3 < 0.0);
     return true;
 }

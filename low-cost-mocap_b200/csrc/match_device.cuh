@@ -65,8 +65,12 @@ __device__ __forceinline__ int decode_group(const WarpState& ws, int C, int KC, 
     for (int i = rc + 1; i < C; ++i) {
         const int k = ws.ncand[r * C + i];
         if (k > 0) {
-            const int d = rem % k;
-            rem /= k;
+            int d = 0;
+            if (k > 1) {                                           // most cameras offer a single candidate: no division
+                const uint32_t qd = rem / (uint32_t)k;
+                d = (int)(rem - qd * (uint32_t)k);
+                rem = qd;
+            }
             cams[nv] = i;
             pts[nv] = ws.cand[((size_t)r * C + i) * KC + d];
             ++nv;
