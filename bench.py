@@ -6,15 +6,21 @@
 One "step" = one pass of the hot path (S1 blob detection -> S2 epipolar matching -> S3 DLT
 triangulation + reprojection error, one launch group per batch) over one batch of synthetic
 frame-sets.  Workload at N = 1: BASELINE config 2 -- 4 cameras, 4 markers, 10 000 frame-sets of
-640x480 uint8 per step, resident in HBM (12.3 GB >> L2, so every step reads HBM).  N > 1:
-one process per GPU (torchrun), every rank owns its own 10 000-frame-set shard of the stream
-(round-robin ownership, weak scaling) and the ranks exchange ONE NCCL all-gather of 3D track
-records per batch.
+640x480 uint8 per step, resident in HBM (12.3 GB >> L2, so every step reads HBM; the batch cycles
+through 4096 distinct frame-sets rendered on the device).  N > 1: one process per GPU (torchrun),
+every rank owns its own 10 000-frame-set shard of the stream (round-robin ownership, weak scaling)
+and the ranks exchange ONE NCCL all-gather of 3D track records per batch.
+--workload c8m16: 8 cameras, 16 markers, 4000 distinct frame-sets per GPU per step -- at N = 1
+BASELINE config 3 (S1-S3 plus one bundle adjustment S4 per 1000 frame-sets, all on the device), at
+N > 1 config 4 (S1-S3 + the all-gather).  Every rank asserts that the timed batch carries no
+overflow flag, checks its first frame-sets against the oracle and (config 3) that S4 converged to
+the true rig; a failed check fails the run.
 
 Printed JSON line (rank 0): value = whole-job frame-sets/s with inputs resident in HBM;
 e2e = the same through the host-buffer C-ABI call (pinned host frames, H2D + D2H inside the
-timed region); roofline = the dominant kernel (k_threshold_segments) against the measured HBM
-peak; cpu_baseline = the oracle port (the reference's own cv2/numpy/scipy call sequence) on
+timed region); roofline = the dominant kernel (k_pipeline_fused, or the stream kernel of the
+three-kernel pipeline on heavy frame-sets) against the measured HBM peak, traffic from the
+committed ncu capture while the kernels are the ones that were profiled; cpu_baseline = the oracle port (the reference's own cv2/numpy/scipy call sequence) on
 this box's host cores on a bounded sample.
 
 --impl reference times the reference's CPU implementation (oracle port: the reference is
@@ -298,14 +304,18 @@ def render_pool_on_device(torch, dev, n_sets, seed, chunk=256):
     return frames, truth, st.poses, st.K
 
 
+# the sources the S1-S3 kernels (the ones a roofline.traffic figure belongs to) are built from
+STREAM_KERNEL_SOURCES = ("common.cuh", "geom.cuh", "blob_device.cuh", "match_device.cuh", "fused_common.cuh", "fused_device.cuh",
+                         "fused_kernel.cu", "blob_kernels.cu", "match_kernels.cu")
+
+
 def csrc_hash():
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "low-cost-mocap_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".h")):
-            with open(os.path.join(d, f), "rb") as fh:
-                h.update(f.encode()); h.update(fh.read())
+    for f in STREAM_KERNEL_SOURCES:
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(f.encode()); h.update(fh.read())
     return h.hexdigest()[:16]
 
 

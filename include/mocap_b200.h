@@ -65,10 +65,11 @@ extern "C" {
 #define MOCAP_F_ROOTS     4   /* more roots than max_roots                               */
 #define MOCAP_F_CANDS     8   /* more than max_cands candidates on one epipolar line     */
 #define MOCAP_F_GROUPS   16   /* more than max_groups candidate groups for one root      */
-#define MOCAP_F_HOLES    32   /* per image, not an overflow: a blob of this image has a hole.  cv.findContours(RETR_TREE)
-                                 (helpers.py:147) emits one more contour -- one more point -- per hole and takes the outer
-                                 contour's moments over the FILLED blob; this library reports one centre per blob from its set
-                                 pixels.  On solid blobs (every parity vector) the two agree exactly; the bit says where not. */
+#define MOCAP_F_HOLES    32   /* per image, not an overflow.  Blobs with holes are reproduced as cv.findContours(RETR_TREE) +
+                                 cv.moments treat them (helpers.py:147-158): one more contour -- one more point -- per hole, the
+                                 outer contour's moments over the FILLED blob, cv2's hierarchy order.  The bit is left only
+                                 when that slow path could not run: a holed blob wider or taller than 62 pixels, or more
+                                 than 64 holes in the image; the image then carries one centre per blob from its set pixels. */
 
 #if defined(__GNUC__)
 #define MOCAP_API __attribute__((visibility("default")))

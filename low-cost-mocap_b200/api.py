@@ -38,8 +38,9 @@ def raise_on_overflow(flags, what):
     capacity would differ from it silently, so the mirrors turn any MOCAP_F_* bit into an error."""
     flags = int(flags)
     if flags & F_HOLES:
-        raise MocapError(-1, f"{what}: a blob has a hole; cv.findContours(RETR_TREE) would give the hole a contour (one more "
-                             f"point) and fill the outer one -- not reproduced by this library (MOCAP_F_HOLES)")
+        raise MocapError(-1, f"{what}: a blob with a hole is too large for the RETR_TREE slow path (wider or taller than 62 pixels, "
+                             f"or more than 64 holes in the image); cv.findContours would give each hole a contour of its own "
+                             f"and fill the outer one (MOCAP_F_HOLES)")
     if flags:
         names = [n for b, n in _FLAG_NAMES.items() if flags & b]
         raise MocapError(-1, f"{what}: capacity overflow ({', '.join(names)}); results would be truncated "

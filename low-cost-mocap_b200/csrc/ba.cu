@@ -742,7 +742,7 @@ int mocap_bundle_adjust_host(mocap_ctx* ctx, const double* obs, const uint8_t* m
 
     // after the prefit the start is already close: begin the polish with a trust region of 0.01 (rad / pose
     // units) instead of scipy's ||x0|| (~ the focal length), which would burn its evaluations shrinking
-    trf::Options topt{opt.ftol, opt.xtol, opt.gtol, opt.max_nfev, opt.prefit ? 1e-2 : 0.0};
+    trf::Options topt{opt.ftol, opt.xtol, opt.gtol, opt.max_nfev, opt.prefit ? BA_POLISH_RADIUS : 0.0};
     trf::Report trep{};
     st = trf::minimize(P, x.data(), topt, trep);
     if (st) return st;

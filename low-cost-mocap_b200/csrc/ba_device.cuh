@@ -31,6 +31,14 @@
 // host-stepped solve in ba.cu): the polish that follows works on a float32-quantised objective whose resolution is
 // coarser than that
 #define BA_PREFIT_REL_STOP 1e-7
+// trust radius the polish starts with after a prefit (rad / pose units; scipy would start at ||x0|| ~ the focal length and
+// spend its evaluations shrinking).  The prefit ends within ~1e-5 of the reference objective's own minimiser, and scipy's
+// radius doubles whenever a step at the boundary is good, so a small start costs nothing when more room is needed;
+// measured on the three S4 goldens: 1e-2 -> 7 evaluations, 1e-4 -> 4, final costs equal to 1e-4 relative (the float32
+// resolution of the objective).  -DBA_POLISH_RADIUS=... overrides it (host-run experiments).
+#ifndef BA_POLISH_RADIUS
+#define BA_POLISH_RADIUS 1e-4
+#endif
 #define BA_TILE 32                 // points per tile (one warp = one column of a tile in the finite-difference pass)
 #define BA_MAX_N (6 * (MOCAP_MAX_CAM - 1))
 
@@ -1212,7 +1220,7 @@ BA_DEV void ba_solve_body(const BAParams& P, unsigned char* smem) {
         ctl->cost = P.fin[npair + n]; ctl->finite = P.fin[npair + n + 1] == 0.0;
         if (!P.prefit) ctl->cost_initial = ctl->cost;
         ctl->nfev = 1; ctl->njev = 1;
-        double D = P.prefit ? 1e-2 : ba_norm2_serial(S.x, nf);     // after the prefit the start is already close (ba.cu)
+        double D = P.prefit ? BA_POLISH_RADIUS : ba_norm2_serial(S.x, nf);     // after the prefit the start is already close (ba.cu)
         if (D == 0.0) D = 1.0;
         ctl->Delta = D; ctl->alpha = 0.0; ctl->iteration = 0; ctl->termination = -99;
         if (!ctl->finite) ctl->termination = -1;

@@ -3,6 +3,7 @@
 // (sort, runs, union-find, 2x2-cell polygon moments).  See blob_kernels.cu for the semantics.
 #pragma once
 #include "common.cuh"
+#include "blob_holes.cuh"
 
 #define SEG_PAD 0xFFFFFFFFu
 
@@ -142,6 +143,7 @@ struct BlobSmem {
     unsigned* wsum;       // [32]
     uint16_t* rowfirst;   // [row_cap] index of the first segment of row (rmin + k), 0xFFFF = empty; nullptr = binary search
     int row_cap;
+    HoleScratch* hs;      // full-size (CTA) reduction only: scratch of the RETR_TREE slow path (blob_holes.cuh); else nullptr
 };
 // index of the first segment with position >= pos (pos lies in row pos / SPR): through the per-row index
 // when the image's rows fit it (one load + a scan over that row's few segments), else by binary search
@@ -156,7 +158,7 @@ __device__ __forceinline__ int row_lower_bound(const BlobSmem& sm, int n, int SP
 }
 
 inline size_t blob_reduce_smem_bytes(int E) {
-    return (size_t)E * (4 + 4 + 2 + 2 + 2 + 2) + (size_t)MOCAP_ACC_CAP * 32 + 32 * 4;
+    return (size_t)E * (4 + 4 + 2 + 2 + 2 + 2) + (size_t)MOCAP_ACC_CAP * 32 + 32 * 4 + sizeof(HoleScratch) + 16;
 }
 __device__ __forceinline__ BlobSmem carve_blob_smem(unsigned char* raw, int E) {
     BlobSmem s;
@@ -167,7 +169,9 @@ __device__ __forceinline__ BlobSmem carve_blob_smem(unsigned char* raw, int E) {
     s.base = reinterpret_cast<uint16_t*>(raw);               raw += (size_t)E * 2;
     s.node_seg = reinterpret_cast<uint16_t*>(raw);           raw += (size_t)E * 2;
     s.node_bits = reinterpret_cast<uint16_t*>(raw);          raw += (size_t)E * 2;
-    s.rank = reinterpret_cast<uint16_t*>(raw);
+    s.rank = reinterpret_cast<uint16_t*>(raw);                raw += (size_t)E * 2;
+    raw += (16 - (reinterpret_cast<uintptr_t>(raw) & 15)) & 15;
+    s.hs = reinterpret_cast<HoleScratch*>(raw);
     s.rowfirst = nullptr; s.row_cap = 0;
     return s;
 }
@@ -176,6 +180,199 @@ __device__ __forceinline__ BlobSmem carve_blob_smem(unsigned char* raw, int E) {
 template <bool WIDE>
 __device__ __forceinline__ unsigned long long acc_get(const unsigned long long* acc, unsigned idx) {
     return WIDE ? acc[idx] : (unsigned long long)reinterpret_cast<const unsigned*>(acc)[idx];
+}
+
+template <bool WIDE>
+__device__ __forceinline__ void acc_add(unsigned long long* acc, unsigned idx, long long v) {
+    if (WIDE) acc[idx] += (unsigned long long)v; else reinterpret_cast<unsigned*>(acc)[idx] += (unsigned)v;
+}
+// Euler number of blob k (kept above the pixel count in accumulator slot 3)
+template <bool WIDE>
+__device__ __forceinline__ int acc_euler(const unsigned long long* acc, unsigned k) {
+    const unsigned long long a3 = acc_get<WIDE>(acc, 4 * k + 3);
+    return WIDE ? (int)(long long)(a3 >> 32) : ((int)((unsigned)a3 >> 20) << 20) >> 20;      // sign-extended
+}
+
+// RETR_TREE for an image that has a blob with a hole (see blob_holes.cuh).  Whole CTA; runs after the blobs' own
+// moments are in sm.acc.  Emits the image's points itself (in cv2's hierarchy order).
+template <int NT, bool WIDE>
+__device__ __noinline__ void blob_holes_cta(BlobSmem sm, int n, unsigned n_runs, unsigned nb, int W, int H, int max_blobs,
+                                            int32_t* __restrict__ out_xy, int32_t* __restrict__ out_n,
+                                            int64_t* __restrict__ out_mom, int32_t* __restrict__ out_flags, int flags) {
+    const int tid = threadIdx.x % NT;
+    const int SPR = W / MOCAP_SEG_PX;
+    HoleScratch& hs = *sm.hs;
+    // first pixel of every blob (its root run is its first run in raster order)
+    for (unsigned id = tid; id < n_runs; id += NT) {
+        if (sm.parent[id] != id) continue;
+        const unsigned k = sm.rank[id];
+        if (k >= nb) continue;
+        const uint32_t p = sm.seg[sm.node_seg[id] & 0x7fff] >> 16;
+        const int y = p / SPR, sc = p - y * SPR;
+        hs.bfirst[k] = (uint32_t)(y * W + 16 * sc + __ffs((int)sm.node_bits[id]) - 1);
+        hs.bparent[k] = -1; hs.bbest[k] = 0xffffffffu;
+    }
+    if (tid == 0) { hs.nholes = 0; hs.unsupported = 0; }
+    __syncthreads();
+    for (unsigned k = 0; k < nb; ++k) {
+        if (acc_euler<WIDE>(sm.acc, k) == 1) continue;               // a solid blob (CTA-uniform)
+        if (tid == 0) { hs.bbox[0] = 1 << 30; hs.bbox[1] = 1 << 30; hs.bbox[2] = -1; hs.bbox[3] = -1; }
+        __syncthreads();
+        for (unsigned id = tid; id < n_runs; id += NT) {
+            if (sm.rank[sm.parent[id]] != k) continue;
+            const uint32_t p = sm.seg[sm.node_seg[id] & 0x7fff] >> 16;
+            const int y = p / SPR, sc = p - y * SPR;
+            const unsigned rb = sm.node_bits[id];
+            atomicMin(&hs.bbox[0], 16 * sc + __ffs((int)rb) - 1);
+            atomicMax(&hs.bbox[2], 16 * sc + 31 - __clz((int)rb));
+            atomicMin(&hs.bbox[1], y);
+            atomicMax(&hs.bbox[3], y);
+        }
+        __syncthreads();
+        const int x0 = hs.bbox[0], y0 = hs.bbox[1], w = hs.bbox[2] - x0 + 1, h = hs.bbox[3] - y0 + 1;
+        if (w + 2 > HOLE_WIN || h + 2 > HOLE_WIN) {                  // does not fit the window: left as the fast path has it
+            if (tid == 0) hs.unsupported = 1;
+            __syncthreads();
+            continue;
+        }
+        for (int r = tid; r < HOLE_WIN; r += NT) { hs.FS[r] = 0ull; hs.Ex[r] = 0ull; hs.Hm[r] = 0ull; hs.Fh[r] = 0ull; }
+        __syncthreads();
+        for (unsigned id = tid; id < n_runs; id += NT) {
+            if (sm.rank[sm.parent[id]] != k) continue;
+            const uint32_t p = sm.seg[sm.node_seg[id] & 0x7fff] >> 16;
+            const int y = p / SPR, sc = p - y * SPR;
+            const unsigned long long rb = sm.node_bits[id];
+            const int sh = 16 * sc + 1 - x0;                         // window bit of the segment's pixel 0
+            atomicOr(&hs.FS[y - y0 + 1], sh >= 0 ? (rb << sh) : (rb >> (-sh)));
+        }
+        __syncthreads();
+        if (tid < 32) {                                              // one warp from here; the others wait at the barrier below
+            const int lane = tid;
+            const unsigned long long Wm = (w + 2 == 64) ? ~0ull : ((1ull << (w + 2)) - 1ull);
+            // the complement of the blob inside the window, kept in Ex's place holder Hm while Ex grows
+            for (int r = lane; r < HOLE_WIN; r += 32) {
+                const unsigned long long fr = r <= h + 1 ? (~hs.FS[r] & Wm) : 0ull;
+                hs.Hm[r] = fr;                                                      // "allowed" for the exterior flood
+                hs.Ex[r] = (r == 0 || r == h + 1) ? fr : (r <= h ? (fr & (1ull | (1ull << (w + 1)))) : 0ull);
+            }
+            __syncwarp();
+            hole_flood(hs.Ex, hs.Hm, h + 1, lane);
+            for (int r = lane; r < HOLE_WIN; r += 32) hs.Hm[r] &= ~hs.Ex[r];         // what the outside does not reach
+            __syncwarp();
+            const long long sA2 = (long long)acc_get<WIDE>(sm.acc, 4 * k), sSX6 = (long long)acc_get<WIDE>(sm.acc, 4 * k + 1);
+            const long long sSY6 = (long long)acc_get<WIDE>(sm.acc, 4 * k + 2);
+            long long addA2 = 0, addSX6 = 0, addSY6 = 0;
+            while (true) {
+                // the first pixel, in raster order, of the regions still to be labelled
+                unsigned key = 0xffffffffu;
+                for (int r = lane; r <= h; r += 32)
+                    if (hs.Hm[r]) { key = min(key, (unsigned)(r * 64 + __ffsll((long long)hs.Hm[r]) - 1)); }
+#pragma unroll 1
+                for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+                if (key == 0xffffffffu) break;
+                const int j = hs.nholes;
+                if (j >= HOLE_CAP) { if (lane == 0) hs.unsupported = 1; break; }
+                const int r0 = (int)(key >> 6), b0 = (int)(key & 63u);
+                for (int r = lane; r < HOLE_WIN; r += 32) hs.Fh[r] = (r == r0) ? (1ull << b0) : 0ull;
+                __syncwarp();
+                hole_flood(hs.Fh, hs.Hm, h + 1, lane);
+                long long size = 0;
+                for (int r = lane; r < HOLE_WIN; r += 32) { size += __popcll(hs.Fh[r]); hs.Hm[r] &= ~hs.Fh[r]; }
+                size = hole_warp_sum(size);
+                long long uA2, uSX6, uSY6;
+                hole_cellsum(hs.FS, hs.Fh, h, x0, y0, lane, uA2, uSX6, uSY6);
+                const long long hA2 = uA2 - sA2, hSX6 = uSX6 - sSX6, hSY6 = uSY6 - sSY6;
+                addA2 += hA2; addSX6 += hSX6; addSY6 += hSY6;
+                // blobs whose first pixel lies in this region: the innermost such region is their parent
+                for (unsigned t = lane; t < nb; t += 32) {
+                    if (t == k) continue;
+                    const int ty = (int)(hs.bfirst[t] / (uint32_t)W), tx = (int)(hs.bfirst[t] - (uint32_t)ty * (uint32_t)W);
+                    const int wr = ty - y0 + 1, wb = tx - x0 + 1;
+                    if (wr >= 0 && wr < HOLE_WIN && wb >= 0 && wb < HOLE_WIN && ((hs.Fh[wr] >> wb) & 1ull) && (uint32_t)size < hs.bbest[t]) {
+                        hs.bbest[t] = (uint32_t)size; hs.bparent[t] = (int16_t)j;
+                    }
+                }
+                if (lane == 0) {
+                    hs.hA2[j] = hA2; hs.hSX6[j] = hSX6; hs.hSY6[j] = hSY6;
+                    hs.hstart[j] = (uint32_t)((y0 - 1 + r0) * W + (x0 - 1 + b0)); hs.hsize[j] = (uint32_t)size; hs.hblob[j] = (uint16_t)k;
+                    hs.nholes = j + 1;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) {                                         // the blob's outer contour runs around the FILLED blob
+                acc_add<WIDE>(sm.acc, 4 * k, addA2); acc_add<WIDE>(sm.acc, 4 * k + 1, addSX6); acc_add<WIDE>(sm.acc, 4 * k + 2, addSY6);
+            }
+        }
+        __syncthreads();
+    }
+    // emission in cv2's order (one thread: this is the slow path; a few dozen items)
+    if (tid == 0) {
+        int count = 0;
+        if (hs.unsupported) {
+            // as the fast path: one centre per blob from its own (by now partly filled) moments, reverse raster order
+            for (int k = (int)nb - 1; k >= 0; --k) {
+                const unsigned long long A2 = acc_get<WIDE>(sm.acc, 4 * k);
+                if (!A2) continue;
+                if (count < max_blobs) {
+                    const double m00 = (double)A2 * 0.5, m10 = (double)acc_get<WIDE>(sm.acc, 4 * k + 1) * 0.16666666666666666;
+                    const double m01 = (double)acc_get<WIDE>(sm.acc, 4 * k + 2) * 0.16666666666666666;
+                    out_xy[2 * count] = (int)(m10 / m00); out_xy[2 * count + 1] = (int)(m01 / m00);
+                    if (out_mom) {
+                        out_mom[4 * count] = (int64_t)A2; out_mom[4 * count + 1] = (int64_t)acc_get<WIDE>(sm.acc, 4 * k + 1);
+                        out_mom[4 * count + 2] = (int64_t)acc_get<WIDE>(sm.acc, 4 * k + 2);
+                        out_mom[4 * count + 3] = (int64_t)(acc_get<WIDE>(sm.acc, 4 * k + 3) & (WIDE ? 0xffffffffull : 0xfffffull));
+                    }
+                }
+                ++count;
+            }
+            flags |= MOCAP_F_HOLES;
+        } else {
+            // pre-order walk of the hierarchy without recursion: a frame lists either the blobs inside hole `owner`
+            // (owner = -1: top level) or the holes of blob `owner`; siblings leave in descending order of their first
+            // pixel, found by scanning for the largest key below the one emitted last
+            struct Frame { int kind, owner; unsigned long long last; };
+            Frame st[34];
+            int sp = 0;
+            st[0].kind = 0; st[0].owner = -1; st[0].last = ~0ull;
+            while (sp >= 0) {
+                Frame& f = st[sp];
+                int best = -1;
+                unsigned long long bkey = 0;
+                if (f.kind == 0) {
+                    for (int t = 0; t < (int)nb; ++t)
+                        if (hs.bparent[t] == f.owner && (unsigned long long)hs.bfirst[t] < f.last && (best < 0 || hs.bfirst[t] > bkey)) { best = t; bkey = hs.bfirst[t]; }
+                } else {
+                    for (int j = 0; j < hs.nholes; ++j)
+                        if (hs.hblob[j] == f.owner && (unsigned long long)hs.hstart[j] < f.last && (best < 0 || hs.hstart[j] > bkey)) { best = j; bkey = hs.hstart[j]; }
+                }
+                if (best < 0) { --sp; continue; }
+                f.last = bkey;
+                long long A2, SX6, SY6, npix;
+                if (f.kind == 0) {
+                    A2 = (long long)acc_get<WIDE>(sm.acc, 4 * best); SX6 = (long long)acc_get<WIDE>(sm.acc, 4 * best + 1);
+                    SY6 = (long long)acc_get<WIDE>(sm.acc, 4 * best + 2);
+                    npix = (long long)(acc_get<WIDE>(sm.acc, 4 * best + 3) & (WIDE ? 0xffffffffull : 0xfffffull));
+                } else { A2 = hs.hA2[best]; SX6 = hs.hSX6[best]; SY6 = hs.hSY6[best]; npix = hs.hsize[best]; }
+                if (A2 != 0) {                                       // helpers.py:153: contours of zero area are dropped
+                    if (count < max_blobs) {
+                        const double m00 = (double)A2 * 0.5, m10 = (double)SX6 * 0.16666666666666666, m01 = (double)SY6 * 0.16666666666666666;
+                        out_xy[2 * count] = (int)(m10 / m00); out_xy[2 * count + 1] = (int)(m01 / m00);
+                        if (out_mom) { out_mom[4 * count] = A2; out_mom[4 * count + 1] = SX6; out_mom[4 * count + 2] = SY6; out_mom[4 * count + 3] = npix; }
+                    }
+                    ++count;
+                }
+                if (sp + 1 < 34) {                                   // descend: a blob's holes, a hole's blobs
+                    ++sp;
+                    st[sp].kind = f.kind == 0 ? 1 : 0; st[sp].owner = best; st[sp].last = ~0ull;
+                }
+            }
+            flags &= ~MOCAP_F_HOLES;
+        }
+        if (count > max_blobs) flags |= MOCAP_F_BLOBS;
+        *out_n = count < max_blobs ? count : max_blobs;
+        if (out_flags) *out_flags = flags;
+    }
+    __syncthreads();
 }
 
 // Returns false (group-uniform) without writing anything when STRICT and a capacity (runs > E,
@@ -480,7 +677,14 @@ __device__ __noinline__ bool blob_reduce(BlobSmem sm, int n, int E, int ACC, int
         // cv.findContours(RETR_TREE) gives every hole a contour of its own (one more point, helpers.py:147-158) and
         // the outer contour's moments are those of the FILLED blob: this path reports the set pixels' polygon and
         // says so
-        if (holed) flags |= MOCAP_F_HOLES;
+        if (holed) {
+            if (STRICT) return false;                    // the one-warp path hands the image to the full-size reduction
+            if (NT > 32 && sm.hs != nullptr) {           // RETR_TREE slow path (blob_holes.cuh); it emits the image itself
+                blob_holes_cta<NT, WIDE>(sm, n, n_runs, nb, W, H, max_blobs, out_xy, out_n, out_mom, out_flags, flags);
+                return true;
+            }
+            flags |= MOCAP_F_HOLES;
+        }
         n_keep = carry;
         carry = 0;
         for (unsigned k0 = 0; k0 < nb; k0 += NT) {      // pass 2: place

@@ -132,7 +132,7 @@ k_blob_reduce_warp(uint32_t* __restrict__ seg_count, const uint32_t* __restrict_
         WarpSlab& sl = slabs[warp];
         BlobSmem sm;
         sm.seg = sl.seg; sm.parent = sl.parent; sm.base = sl.base; sm.node_seg = sl.node_seg;
-        sm.node_bits = sl.node_bits; sm.rank = sl.rank; sm.acc = sl.acc; sm.wsum = nullptr;
+        sm.node_bits = sl.node_bits; sm.rank = sl.rank; sm.acc = sl.acc; sm.wsum = nullptr; sm.hs = nullptr;
         sm.rowfirst = BLOB_ROWFIRST(sl, WIDE); sm.row_cap = WIDE ? 0 : BLOB_ROWS;
         const uint32_t* src = seg_list + (size_t)img * E;
         for (int i = lane; i < (int)cnt; i += 32) sm.seg[i] = src[i];

@@ -58,7 +58,7 @@ __device__ __forceinline__ int phased_reduce_image(const FusedParams& P, unsigne
             WarpSlab& sl = *reinterpret_cast<WarpSlab*>(slab);
             BlobSmem sm;
             sm.seg = sl.seg; sm.parent = sl.parent; sm.base = sl.base; sm.node_seg = sl.node_seg;
-            sm.node_bits = sl.node_bits; sm.rank = sl.rank; sm.acc = sl.acc; sm.wsum = nullptr;
+            sm.node_bits = sl.node_bits; sm.rank = sl.rank; sm.acc = sl.acc; sm.wsum = nullptr; sm.hs = nullptr;
             sm.rowfirst = BLOB_ROWFIRST(sl, WIDE); sm.row_cap = WIDE ? 0 : BLOB_ROWS;
             const uint32_t* lst = P.seg_list + (size_t)img * P.E;
             for (int i = lane; i < (int)cnt; i += 32) sm.seg[i] = __ldcg(lst + i);

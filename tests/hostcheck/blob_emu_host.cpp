@@ -49,7 +49,7 @@ int reduce_image(const std::vector<uint32_t>& list, int W, int H, int max_blobs,
         simt::launch(32, [&] {
             BlobSmem sm;
             sm.seg = slab.seg; sm.parent = slab.parent; sm.base = slab.base; sm.node_seg = slab.node_seg;
-            sm.node_bits = slab.node_bits; sm.rank = slab.rank; sm.acc = slab.acc; sm.wsum = nullptr;
+            sm.node_bits = slab.node_bits; sm.rank = slab.rank; sm.acc = slab.acc; sm.wsum = nullptr; sm.hs = nullptr;
             sm.rowfirst = BLOB_ROWFIRST(slab, WIDE); sm.row_cap = WIDE ? 0 : BLOB_ROWS;
             const int lane = threadIdx.x & 31;
             for (int i = lane; i < cnt; i += 32) sm.seg[i] = list[i];

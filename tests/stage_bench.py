@@ -73,7 +73,7 @@ def colour_pipeline():
     ms = timed(lambda: ctx.pipeline(colour, out=out3))
     valid = torch.arange(out1["obj"].shape[1], device="cuda")[None, :] < out1["n"][:, None]
     same = bool(torch.equal(out1["n"], out3["n"]) and torch.equal(out1["obj"][valid], out3["obj"][valid]))
-    return {"workload": "4 cameras, 4 markers, 2000 frame-sets of 640x480x3 interleaved (7.4 GB resident), three-kernel path",
+    return {"workload": "4 cameras, 4 markers, 2000 frame-sets of 640x480x3 interleaved (7.4 GB resident), " + ("three-kernel path" if os.environ.get("MOCAP_PIPELINE") == "split" else "single-pass kernel"),
             "ms_per_batch": ms, "frame_sets_per_s": B / ms * 1e3, "hbm_gbs": B * C * 921600 / ms / 1e6,
             "equals_one_channel_run": same}
 

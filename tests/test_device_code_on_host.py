@@ -525,48 +525,63 @@ def test_ba_kernel_on_host_with_prefit_beats_the_reference(ba_emu):
     assert np.allclose(R1[0], np.eye(3)) and np.allclose(t1[0], 0)
 
 
-def test_blob_device_code_flags_blobs_with_holes(blob_emu):
-    """cv.findContours(RETR_TREE) (helpers.py:147) emits a contour per hole; the device code reports one centre per
-    blob and must say so: MOCAP_F_HOLES is set exactly for the images in which cv2 finds a hole contour.  Random
-    blobs (rings, blobs with several holes, nested blobs, holes touching diagonally, 1-px walls, blobs across the
-    16-px segment boundaries and at the image border), both variants of the device function."""
+def test_blob_device_code_reproduces_retr_tree_on_blobs_with_holes(blob_emu):
+    """cv.findContours(RETR_TREE) (helpers.py:147) emits a contour per hole, takes the outer contour's moments over the
+    FILLED blob and orders the contours along its hierarchy.  The one-warp path hands an image whose Euler numbers show
+    a hole to the full-size reduction, which runs the RETR_TREE slow path (csrc/blob_holes.cuh): the emitted points
+    -- count, values and order -- equal cv2's on random images with rings, frames, porous patches, blobs inside holes,
+    rings inside rings, holes touching diagonally, 1-px walls, blobs across the 16-px segment boundaries and at the
+    image border; no flag is left.  A holed blob too large for the slow path's window keeps MOCAP_F_HOLES."""
     import cv2
     rng = np.random.default_rng(31)
     H, W = 96, 128
+
+    def reference(img):
+        contours, hier = cv2.findContours((img > 51).astype(np.uint8), cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+        out = []
+        for cnt in contours:
+            m = cv2.moments(cnt)
+            if m["m00"] != 0:
+                out.append([int(m["m10"] / m["m00"]), int(m["m01"] / m["m00"])])
+        has_hole = hier is not None and any(h[3] >= 0 for h in hier[0])
+        return out, has_hole
     seen = {True: 0, False: 0}
-    for trial in range(60):
+    for trial in range(50):
         img = np.zeros((H, W), np.uint8)
-        for _ in range(rng.integers(1, 6)):
+        for _ in range(rng.integers(1, 7)):
             cx, cy = int(rng.integers(0, W)), int(rng.integers(0, H))
-            kind = rng.integers(0, 5)
+            kind = rng.integers(0, 6)
             if kind == 0:
-                cv2.circle(img, (cx, cy), int(rng.integers(2, 9)), 255, int(rng.integers(1, 3)))          # ring
+                cv2.circle(img, (cx, cy), int(rng.integers(2, 10)), 255, int(rng.integers(1, 3)))          # ring
             elif kind == 1:
                 cv2.circle(img, (cx, cy), int(rng.integers(1, 7)), 255, -1)                                # disc
             elif kind == 2:
                 w, h = int(rng.integers(3, 24)), int(rng.integers(3, 12))
                 cv2.rectangle(img, (cx, cy), (cx + w, cy + h), 255, 1)                                     # frame (may cross segments)
                 if rng.integers(0, 2):
-                    cv2.circle(img, (cx + w // 2, cy + h // 2), 1, 255, -1)                                # nested blob
+                    cv2.circle(img, (cx + w // 2, cy + h // 2), 1, 255, -1)                                # blob inside the hole
             elif kind == 3:
                 m = (rng.uniform(size=(9, 14)) < 0.72).astype(np.uint8) * 255                              # porous patch
                 y0, x0 = min(cy, H - 9), min(cx, W - 14)
                 img[y0:y0 + 9, x0:x0 + 14] = np.maximum(img[y0:y0 + 9, x0:x0 + 14], m)
+            elif kind == 4:
+                cv2.circle(img, (cx, cy), int(rng.integers(6, 12)), 255, 1)                                # ring inside a ring
+                cv2.circle(img, (cx, cy), int(rng.integers(2, 4)), 255, 1)
             else:
                 img[max(cy - 2, 0):cy + 3, max(cx - 2, 0):cx + 3] = 255
                 img[cy, cx] = 0 if rng.integers(0, 2) else 255                                            # 1-px hole
-        contours, hier = cv2.findContours((img > 51).astype(np.uint8), cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
-        if hier is None:
-            continue
-        # with RETR_TREE the contours at odd nesting depth are the hole borders
-        depth = lambda i: 0 if hier[0][i][3] < 0 else 1 + depth(hier[0][i][3])
-        has_hole = any(depth(i) % 2 == 1 for i in range(len(contours)))
+        ref, has_hole = reference(img)
         seen[has_hole] += 1
         for force_cta in (0, 1):
             d = blob_emu(img, force_cta=force_cta, seed=trial)
-            assert bool(d["flags"] & 32) == has_hole, (trial, force_cta, d["flags"])
-            assert d["flags"] & ~32 == 0
-    assert seen[True] >= 15 and seen[False] >= 5
+            assert d["flags"] == 0 and d["xy"].tolist() == ref, (trial, force_cta, d["flags"])
+            if has_hole:
+                assert d["path"] == 2                    # the slow path lives in the full-size reduction
+    assert seen[True] >= 15                           # (solid-only images are what every other blob test covers)
+    big = np.zeros((H, W), np.uint8)
+    cv2.circle(big, (64, 48), 40, 255, 2)                # an 84-px ring: wider than the 62-px window
+    d = blob_emu(big)
+    assert d["flags"] == 32 and d["n"] == 1
 
 
 def test_single_pass_kernel_on_host_three_channel_layout(fused_emu):

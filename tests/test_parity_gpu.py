@@ -1204,39 +1204,45 @@ def test_config3_chain_on_the_device(torch):
         assert np.abs(tn[c] * s - np.asarray(poses[c]["t"]).reshape(3)).max() < 2e-2
 
 
-def test_detect_flags_blobs_with_holes(torch):
+def test_detect_reproduces_retr_tree_on_blobs_with_holes(torch):
     """Blobs with holes (golden blobs_rings: rings, frames, porous patches, nested blobs through the REAL _find_dot):
-    cv.findContours(RETR_TREE) emits an extra contour per hole, this library does not -- MOCAP_F_HOLES must be set on
-    exactly the frames whose contour hierarchy has a hole, through mocap_detect_dev and through both pipelines (where
-    it travels into the frame-set flags); frames without holes agree with the reference exactly; the mirror raises."""
+    cv.findContours(RETR_TREE) emits an extra contour per hole, fills the outer one and orders along its hierarchy.
+    Through mocap_detect_dev and through both pipelines the points -- count, values, order -- equal the real
+    reference's on every frame, with and without holes, and no flag is left; the mirror returns the reference's list.
+    A holed blob too large for the slow path's window is flagged (and the mirror raises)."""
     z = load_golden("blobs_rings")
     frames = z["frames"]                                   # [F, 1, H, W]
     F = frames.shape[0]
-    ctx = _ctx(1, max_blobs=64)
-    d = ctx.detect(torch.from_numpy(frames).cuda())
-    flags = d["flags"].cpu().numpy()
-    n = d["n"].cpu().numpy()
-    xy = d["xy"].cpu().numpy()
-    assert np.array_equal((flags & 32) != 0, z["has_hole"].astype(bool))
     assert int(z["has_hole"].sum()) >= 5 and int((1 - z["has_hole"]).sum()) >= 5
+    kmax = int(z["blob_n"].max())
+    assert kmax <= 64
+    ctx = _ctx(1, max_blobs=64)
+    d = ctx.detect(torch.from_numpy(frames).cuda(), want_moments=True)
+    flags = d["flags"].cpu().numpy(); n = d["n"].cpu().numpy(); xy = d["xy"].cpu().numpy()
     for f in range(F):
-        if not z["has_hole"][f]:
-            k = int(z["blob_n"][f, 0])
-            assert flags[f] == 0 and n[f] == k and np.array_equal(xy[f, :k], z["blob_xy"][f, 0, :k]), f
-    ctx.set_cameras([np.array([[600.0, 0, 320], [0, 600, 240], [0, 0, 1]])], [{"R": np.eye(3), "t": np.zeros(3)}])
+        k = int(z["blob_n"][f, 0])
+        assert flags[f] == 0 and n[f] == k and np.array_equal(xy[f, :k], z["blob_xy"][f, 0, :k]), f
+    K1 = np.array([[600.0, 0, 320], [0, 600, 240], [0, 0, 1]])
     for mode in ("fused", "split"):
         os.environ["MOCAP_PIPELINE"] = mode
         try:
             c2 = _ctx(1, max_blobs=64)
         finally:
             os.environ.pop("MOCAP_PIPELINE", None)
-        c2.set_cameras([np.array([[600.0, 0, 320], [0, 600, 240], [0, 0, 1]])], [{"R": np.eye(3), "t": np.zeros(3)}])
-        out = c2.pipeline(torch.from_numpy(frames).cuda())
-        assert np.array_equal((out["flags"].cpu().numpy() & 32) != 0, z["has_hole"].astype(bool)), mode
+        c2.set_cameras([K1], [{"R": np.eye(3), "t": np.zeros(3)}])
+        for rep in range(2):                               # twice: the deferral path re-arms its worklists
+            out = c2.pipeline(torch.from_numpy(frames).cuda())
+            assert int((out["flags"] != 0).sum().item()) == 0, mode
+        d2 = c2.detect(torch.from_numpy(frames).cuda())
+        assert torch.equal(d2["n"], d["n"]) and torch.equal(d2["xy"], d["xy"])
     s = pkg.MocapSession([np.eye(3)])
-    holed = int(np.argmax(z["has_hole"]))
+    for f in (int(np.argmax(z["has_hole"])), int(np.argmin(z["has_hole"]))):
+        _, pts = pkg.find_dot(as3(frames[f, 0]), session=s)
+        assert pts == z["blob_xy"][f, 0, :int(z["blob_n"][f, 0])].tolist()
+    import cv2
+    big = np.zeros((480, 640), np.uint8)
+    cv2.circle(big, (300, 200), 60, 255, 3)                # a 120-px ring: does not fit the 62-px window
+    db = ctx.detect(torch.from_numpy(big[None]).cuda())
+    assert int(db["flags"][0].item()) == 32 and int(db["n"][0].item()) == 1
     with pytest.raises(pkg.MocapError):
-        pkg.find_dot(as3(frames[holed, 0]), session=s)
-    solid = int(np.argmin(z["has_hole"]))
-    _, pts = pkg.find_dot(as3(frames[solid, 0]), session=s)
-    assert pts == z["blob_xy"][solid, 0, :int(z["blob_n"][solid, 0])].tolist()
+        pkg.find_dot(as3(big), session=s)
