@@ -1214,14 +1214,14 @@ def test_detect_reproduces_retr_tree_on_blobs_with_holes(torch):
     frames = z["frames"]                                   # [F, 1, H, W]
     F = frames.shape[0]
     assert int(z["has_hole"].sum()) >= 5 and int((1 - z["has_hole"]).sum()) >= 5
-    kmax = int(z["blob_n"].max())
-    assert kmax <= 64
     ctx = _ctx(1, max_blobs=64)
     d = ctx.detect(torch.from_numpy(frames).cuda(), want_moments=True)
     flags = d["flags"].cpu().numpy(); n = d["n"].cpu().numpy(); xy = d["xy"].cpu().numpy()
+    fits = z["blob_n"][:, 0] <= 64                         # the library keeps at most 64 points per image (MOCAP_F_BLOBS beyond)
+    assert fits.sum() >= F - 4 and (z["has_hole"].astype(bool) & fits).sum() >= 5
     for f in range(F):
-        k = int(z["blob_n"][f, 0])
-        assert flags[f] == 0 and n[f] == k and np.array_equal(xy[f, :k], z["blob_xy"][f, 0, :k]), f
+        k = min(int(z["blob_n"][f, 0]), 64)
+        assert flags[f] == (0 if fits[f] else 2) and n[f] == k and np.array_equal(xy[f, :k], z["blob_xy"][f, 0, :k]), f
     K1 = np.array([[600.0, 0, 320], [0, 600, 240], [0, 0, 1]])
     for mode in ("fused", "split"):
         os.environ["MOCAP_PIPELINE"] = mode
@@ -1232,11 +1232,11 @@ def test_detect_reproduces_retr_tree_on_blobs_with_holes(torch):
         c2.set_cameras([K1], [{"R": np.eye(3), "t": np.zeros(3)}])
         for rep in range(2):                               # twice: the deferral path re-arms its worklists
             out = c2.pipeline(torch.from_numpy(frames).cuda())
-            assert int((out["flags"] != 0).sum().item()) == 0, mode
+            assert np.array_equal(out["flags"].cpu().numpy() != 0, ~fits), mode
         d2 = c2.detect(torch.from_numpy(frames).cuda())
         assert torch.equal(d2["n"], d["n"]) and torch.equal(d2["xy"], d["xy"])
     s = pkg.MocapSession([np.eye(3)])
-    for f in (int(np.argmax(z["has_hole"])), int(np.argmin(z["has_hole"]))):
+    for f in (int(np.argmax(z["has_hole"].astype(bool) & fits)), int(np.argmax(~z["has_hole"].astype(bool) & fits))):
         _, pts = pkg.find_dot(as3(frames[f, 0]), session=s)
         assert pts == z["blob_xy"][f, 0, :int(z["blob_n"][f, 0])].tolist()
     import cv2
