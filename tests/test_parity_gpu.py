@@ -1221,7 +1221,10 @@ def test_detect_reproduces_retr_tree_on_blobs_with_holes(torch):
     assert fits.sum() >= F - 4 and (z["has_hole"].astype(bool) & fits).sum() >= 5
     for f in range(F):
         k = min(int(z["blob_n"][f, 0]), 64)
+        if not fits[f] and flags[f] == 32:
+            continue                                       # more than 64 holes in one image: left flagged (frame 14 of the golden: 68 holes)
         assert flags[f] == (0 if fits[f] else 2) and n[f] == k and np.array_equal(xy[f, :k], z["blob_xy"][f, 0, :k]), f
+    assert int((flags == 32).sum()) <= 1
     K1 = np.array([[600.0, 0, 320], [0, 600, 240], [0, 0, 1]])
     for mode in ("fused", "split"):
         os.environ["MOCAP_PIPELINE"] = mode
@@ -1232,7 +1235,7 @@ def test_detect_reproduces_retr_tree_on_blobs_with_holes(torch):
         c2.set_cameras([K1], [{"R": np.eye(3), "t": np.zeros(3)}])
         for rep in range(2):                               # twice: the deferral path re-arms its worklists
             out = c2.pipeline(torch.from_numpy(frames).cuda())
-            assert np.array_equal(out["flags"].cpu().numpy() != 0, ~fits), mode
+            assert np.array_equal(out["flags"].cpu().numpy(), flags), mode
         d2 = c2.detect(torch.from_numpy(frames).cuda())
         assert torch.equal(d2["n"], d["n"]) and torch.equal(d2["xy"], d["xy"])
     s = pkg.MocapSession([np.eye(3)])
