@@ -305,7 +305,7 @@ def render_pool_on_device(torch, dev, n_sets, seed, chunk=256):
 
 
 # the sources the S1-S3 kernels (the ones a roofline.traffic figure belongs to) are built from
-STREAM_KERNEL_SOURCES = ("common.cuh", "geom.cuh", "blob_device.cuh", "match_device.cuh", "fused_common.cuh", "fused_device.cuh",
+STREAM_KERNEL_SOURCES = ("common.cuh", "geom.cuh", "blob_device.cuh", "blob_holes.cuh", "match_device.cuh", "fused_common.cuh", "fused_device.cuh",
                          "fused_kernel.cu", "blob_kernels.cu", "match_kernels.cu")
 
 
