@@ -31,7 +31,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         subprocess.check_call(cmd)
         objs.append(obj)
-    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    # link under a temporary name and rename: a reader (or a repository snapshot) never sees a half-written library
+    tmp = LIB + ".tmp"
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    os.replace(tmp, LIB)
     return LIB
 
 
