@@ -443,7 +443,14 @@ def test_phased_kernel_on_host_equals_single_pass_kernel(fused_emu):
     R = np.stack([np.eye(3)] * C); t = np.array([[-0.3 * c, 0.0, 0.0] for c in range(C)])
     a = fused_emu(frames, K, R, t, max_roots=32, runs=2, phased=0)
     b = fused_emu(frames, K, R, t, max_roots=32, runs=2, phased=1)
-    assert b["dirty_scratch"] == 0 and b["deferred_images"] == [] and b["deferred_sets"] == []
+    # the only images that may leave the fast path are the ones holding a blob with a hole (RETR_TREE work, blob_holes.cuh)
+    import cv2
+    holed = []
+    for i, img in enumerate(frames.reshape(B * C, H, W)):
+        _, hier = cv2.findContours(cv2.threshold(img, 255 * 0.2, 255, cv2.THRESH_BINARY)[1], cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+        if hier is not None and (hier[0, :, 3] >= 0).any():
+            holed.append(i)
+    assert b["dirty_scratch"] == 0 and b["deferred_images"] == holed and b["deferred_sets"] == sorted({i // C for i in holed})
     assert np.array_equal(a["blob_n"], b["blob_n"]) and np.array_equal(a["blob_xy"], b["blob_xy"])
     assert np.array_equal(a["n"], b["n"]) and np.array_equal(a["flags"], b["flags"])
     for s in range(B):
