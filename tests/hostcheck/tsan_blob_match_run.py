@@ -12,7 +12,7 @@ from tests.util import load_golden  # noqa: E402
 
 p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
 bl, ml = ctypes.CDLL(blob_lib), ctypes.CDLL(match_lib)
-z = load_golden("pipe_c8_m16")
+z = load_golden("pipe_c8_m16", n=2)
 img = np.ascontiguousarray(z["frames"][0, 0])
 crowd = img.copy()
 for k in range(70):

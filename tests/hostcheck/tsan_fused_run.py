@@ -11,7 +11,7 @@ from tests.util import load_golden  # noqa: E402
 
 lib = ctypes.CDLL(lib_path)
 p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-z = load_golden(case)
+z = load_golden(case, n=4)
 C, B = int(z["C"]), 4
 frames = np.ascontiguousarray(z["frames"][:B])
 phased = 1 if "phased" in sys.argv[4:] else 0
