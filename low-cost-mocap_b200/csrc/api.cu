@@ -147,6 +147,7 @@ void mocap_destroy(mocap_ctx* ctx) {
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_ba_ws);
     cudaFree(ctx->d_match_counter);
+    cudaFree(ctx->d_match_items); cudaFree(ctx->d_match_partial); cudaFree(ctx->d_match_range); cudaFree(ctx->d_match_arrive);
     cudaFree(ctx->d_pp_m1); cudaFree(ctx->d_pp_m2); cudaFree(ctx->d_pp_rot);
     cudaFree(ctx->d_stat_acc);
     if (ctx->h_stat) cudaFreeHost(const_cast<unsigned long long*>(ctx->h_stat));

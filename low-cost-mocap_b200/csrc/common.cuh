@@ -67,7 +67,10 @@ struct mocap_ctx {
     void*     d_scratch; size_t scratch_bytes;
     // S4 on the device (ba_dev.cu): workspace of k_ba_solve, launch shape
     void*     d_ba_ws; size_t ba_ws_bytes; int ba_threads; int ba_grid; size_t ba_smem;
-    unsigned* d_match_counter; int match_ctas_per_sm;   // k_match_triangulate: frame-set claim counter, resident CTAs per SM
+    unsigned* d_match_counter; int match_ctas_per_sm;   // k_match_triangulate: claim counters [4], resident CTAs per SM
+    // chunked matcher (match_device.cuh MatchSplit): items, their partial results, the roots each touches, arrivals per frame-set
+    void* d_match_items; unsigned long long* d_match_partial; int* d_match_range; unsigned* d_match_arrive;
+    int match_chunk, match_item_cap, match_cap_sets;
     const int32_t* img_flags_cur;   // set by the pipelines: the matcher folds the images' S1 flags into the frame-set's
     int32_t*  track_xy_cur;   // set for the duration of mocap_pipeline_tracks_dev: where the matcher leaves the winners' pixels
     // capture-side preprocessing
@@ -105,6 +108,8 @@ int launch_blob_fallback(mocap_ctx* ctx, int32_t* blob_xy, int32_t* blob_n, int6
 // frame-sets with more blobs than this (average of the previous batch) are cheaper through the three-kernel
 // pipeline: the matcher's large code then runs in a kernel of its own instead of evicting the stream loop
 #define MOCAP_HEAVY_BLOBS_PER_SET 48
+// candidate groups per work item of the chunked matcher: frame-sets with more are evaluated by several warps
+#define MOCAP_MATCH_CHUNK 512
 int launch_match_list(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n, const uint32_t* set_list, uint32_t* set_count,
                       int n_sets_max, double* obj, double* err, int32_t* n_obj, int32_t* set_flags);
 int launch_pipeline_tma(mocap_ctx* ctx, const uint8_t* frames, int n_sets, int threshold,

@@ -112,13 +112,17 @@ static __device__ __noinline__ void eval_group(const CameraTables* __restrict__ 
     err = mean_like_numpy(sq, 2 * nv, nv == C);
 }
 
-// One warp: the whole matcher for frame-set `set`.  xy / nb are read with ld.global.cg so that the
-// function may consume blob lists written earlier IN THE SAME KERNEL by other warps (fused pipeline).
-static __device__ __noinline__ void match_triangulate_warp(
-    const CameraTables* __restrict__ tb, WarpState ws, const int32_t* xy, const int32_t* nb, int set, int lane,
-    int C, int MB, int RMAX, int KC, uint32_t GMAX, double* __restrict__ obj, double* __restrict__ err_out,
-    int32_t* __restrict__ n_obj, int32_t* __restrict__ set_flags, int32_t* __restrict__ chosen,
-    int32_t* __restrict__ track_xy = nullptr, const int32_t* img_flags = nullptr) {
+// The matcher of one frame-set is three steps of one warp: prepare (roots, candidate lists, group counts), evaluate a
+// range of the frame-set's candidate groups (per-root best so far in shared memory), emit (winners in root order).
+// match_triangulate_warp runs them back to back; k_match_chunks (match_kernels.cu) gives the middle step of a frame-set
+// with thousands of groups to several warps, one range each.
+struct MatchPrep { int nr; uint32_t total; int flags; };
+
+// xy / nb are read with ld.global.cg so that the function may consume blob lists written earlier IN THE SAME KERNEL by
+// other warps (fused pipeline).  Leaves the staged blob centres in ws.xy_s (every later step reads those).
+static __device__ __forceinline__ MatchPrep match_prepare_warp(
+    const CameraTables* __restrict__ tb, const WarpState& ws, const int32_t* xy, const int32_t* nb, int lane,
+    int C, int MB, int RMAX, int KC, uint32_t GMAX, const int32_t* img_flags) {
     int flags = 0;
     // inside a pipeline: what S1 reported for the frame-set's images (truncated blob lists, blobs with holes) travels
     // with the frame-set
@@ -238,17 +242,24 @@ static __device__ __noinline__ void match_triangulate_warp(
         ws.gprefix[nr] = acc;
     }
     __syncwarp();
-    const uint32_t total = ws.gprefix[nr];
+    MatchPrep prep;
+    prep.nr = nr; prep.total = ws.gprefix[nr]; prep.flags = flags;
+    return prep;
+}
 
-    // pass 1: every group's point and error; segmented warp argmin; the head lane of every root's
-    // segment pulls the winner's point over by shuffle and folds it into shared memory
-    for (uint32_t w0 = 0; w0 < total; w0 += 32) {
+// groups [w_lo, w_hi) of the frame-set (numbered through the roots in order; w_lo a multiple of 32): every group's point
+// and error; segmented warp argmin; the head lane of every root's segment pulls the winner's point over by shuffle and
+// folds it into shared memory.  Ranges evaluated in ascending order give what one pass over [0, total) gives.
+static __device__ __forceinline__ void match_eval_range_warp(
+    const CameraTables* __restrict__ tb, const WarpState& ws, int lane, int C, int MB, int KC, int nr, uint32_t w_lo, uint32_t w_hi) {
+    const int32_t* xy = ws.xy_s;
+    for (uint32_t w0 = w_lo; w0 < w_hi; w0 += 32) {
         const uint32_t w = w0 + lane;
         int r = -1;
         uint32_t g = 0;
         unsigned long long key = ~0ull;
         double X[3] = {0.0, 0.0, 0.0}, e = 0.0;
-        if (w < total) {
+        if (w < w_hi) {
             int lo = 0, hi = nr;                               // last r with gprefix[r] <= w
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ws.gprefix[mid] <= w) lo = mid; else hi = mid; }
             r = lo;
@@ -275,8 +286,14 @@ static __device__ __noinline__ void match_triangulate_warp(
         }
         __syncwarp();
     }
+}
 
-    // pass 2: winners, compacted in root order (helpers.py:413-419 skips roots without a 3D point)
+// winners, compacted in root order (helpers.py:413-419 skips roots without a 3D point)
+static __device__ __forceinline__ void match_emit_warp(
+    const CameraTables* __restrict__ tb, const WarpState& ws, int set, int lane, int C, int MB, int RMAX, int KC, int nr, int flags,
+    double* __restrict__ obj, double* __restrict__ err_out, int32_t* __restrict__ n_obj, int32_t* __restrict__ set_flags,
+    int32_t* __restrict__ chosen, int32_t* __restrict__ track_xy) {
+    const int32_t* xy = ws.xy_s;
     int n_out = 0;
     double* obj_s = obj + (size_t)set * RMAX * 3;
     double* err_s = err_out + (size_t)set * RMAX;
@@ -327,3 +344,148 @@ static __device__ __noinline__ void match_triangulate_warp(
     }
 }
 
+// One warp: the whole matcher for frame-set `set`.
+static __device__ __noinline__ void match_triangulate_warp(
+    const CameraTables* __restrict__ tb, WarpState ws, const int32_t* xy, const int32_t* nb, int set, int lane,
+    int C, int MB, int RMAX, int KC, uint32_t GMAX, double* __restrict__ obj, double* __restrict__ err_out,
+    int32_t* __restrict__ n_obj, int32_t* __restrict__ set_flags, int32_t* __restrict__ chosen,
+    int32_t* __restrict__ track_xy = nullptr, const int32_t* img_flags = nullptr) {
+    const MatchPrep p = match_prepare_warp(tb, ws, xy, nb, lane, C, MB, RMAX, KC, GMAX, img_flags);
+    match_eval_range_warp(tb, ws, lane, C, MB, KC, p.nr, 0u, p.total);
+    match_emit_warp(tb, ws, set, lane, C, MB, RMAX, KC, p.nr, p.flags, obj, err_out, n_obj, set_flags, chosen, track_xy);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Frame-sets with thousands of candidate groups, several warps each.
+//
+// The number of groups of a frame-set is the sum over its roots of the product of the candidate counts per camera: on 8
+// cameras x 16 markers the mean is about 700, one frame-set in a hundred has more than 3000, single roots reach tens of
+// thousands.  One warp evaluates 32 groups per round, so with one warp per frame-set the kernel lasts as long as its
+// heaviest frame-set while most warps idle.  The first kernel therefore finishes only the frame-sets of at most `chunk`
+// groups and cuts every other one into items (frame-set, range of `chunk` groups); the second kernel hands the items to
+// warps.  A warp prepares the frame-set again (cheap: about two rounds' worth), evaluates its range, and leaves the best
+// group of every root the range touches in global memory; the warp that finishes a frame-set's last item folds the items'
+// results together in ascending range order (strict "<": the earliest group wins ties, as np.argmin) and emits.
+// The result is bit-identical to one warp walking the whole frame-set.
+struct MatchItem { uint32_t set, chunk, n_chunks, first; };           // set = ~0u: void (the item list was full)
+#define MATCH_PARTIAL_WORDS 6                                          // key, group, X, Y, Z, error
+struct MatchSplit {
+    unsigned* counters;                // [0] frame-sets claimed, [1] items allocated, [2] items claimed (zeroed before the first kernel)
+    MatchItem* items;                  // [item_cap]; nullptr: every frame-set is finished by the warp that claimed it
+    unsigned long long* partial;       // [item_cap][RMAX][MATCH_PARTIAL_WORDS]
+    int* range;                        // [item_cap][2] first and last root the item's range touches
+    unsigned* arrive;                  // [n_sets] finished items of the frame-set; the finisher re-arms it
+    uint32_t chunk, item_cap;          // chunk: a multiple of 32
+};
+
+// first kernel: persistent warps claim frame-sets from a counter (the work per frame-set varies by orders of magnitude, a
+// static assignment leaves the SMs idle behind the heaviest CTAs)
+static __device__ __forceinline__ void match_sets_body(
+    const CameraTables* __restrict__ tb, const WarpState& ws, int lane, const int32_t* blob_xy, const int32_t* blob_n, int n_sets,
+    int C, int MB, int RMAX, int KC, uint32_t GMAX, const MatchSplit& sp, double* __restrict__ obj, double* __restrict__ err_out,
+    int32_t* __restrict__ n_obj, int32_t* __restrict__ set_flags, int32_t* __restrict__ chosen, int32_t* __restrict__ track_xy,
+    const int32_t* __restrict__ img_flags) {
+    while (true) {
+        unsigned s = 0;
+        if (lane == 0) s = atomicAdd(sp.counters, 1u);
+        s = __shfl_sync(FULL_MASK, s, 0);
+        if (s >= (unsigned)n_sets) break;
+        const int set = (int)s;
+        const MatchPrep p = match_prepare_warp(tb, ws, blob_xy + (size_t)set * C * MB * 2, blob_n + (size_t)set * C, lane, C, MB, RMAX, KC, GMAX,
+                                               img_flags ? img_flags + (size_t)set * C : nullptr);
+        if (sp.items && p.total > sp.chunk) {
+            const uint32_t nch = (p.total + sp.chunk - 1) / sp.chunk;
+            unsigned first = 0;
+            if (lane == 0) first = atomicAdd(sp.counters + 1, nch);
+            first = __shfl_sync(FULL_MASK, first, 0);
+            const bool fits = first <= sp.item_cap && nch <= sp.item_cap - first;
+            for (uint32_t c = lane; c < nch && first + c < sp.item_cap; c += 32) {
+                MatchItem it;
+                it.set = fits ? (uint32_t)set : ~0u; it.chunk = c; it.n_chunks = nch; it.first = first;
+                sp.items[first + c] = it;
+            }
+            if (fits) { __syncwarp(); continue; }
+        }
+        match_eval_range_warp(tb, ws, lane, C, MB, KC, p.nr, 0u, p.total);
+        match_emit_warp(tb, ws, set, lane, C, MB, RMAX, KC, p.nr, p.flags, obj, err_out, n_obj, set_flags, chosen, track_xy);
+        __syncwarp();
+    }
+}
+
+// second kernel: persistent warps claim items
+static __device__ __forceinline__ void match_chunks_body(
+    const CameraTables* __restrict__ tb, const WarpState& ws, int lane, const int32_t* blob_xy, const int32_t* blob_n,
+    int C, int MB, int RMAX, int KC, uint32_t GMAX, const MatchSplit& sp, double* __restrict__ obj, double* __restrict__ err_out,
+    int32_t* __restrict__ n_obj, int32_t* __restrict__ set_flags, int32_t* __restrict__ chosen, int32_t* __restrict__ track_xy,
+    const int32_t* __restrict__ img_flags) {
+    unsigned n_items = __ldcg(sp.counters + 1);                      // final: the first kernel has finished
+    if (n_items > sp.item_cap) n_items = sp.item_cap;
+    while (true) {
+        unsigned i = 0;
+        if (lane == 0) i = atomicAdd(sp.counters + 2, 1u);
+        i = __shfl_sync(FULL_MASK, i, 0);
+        if (i >= n_items) break;
+        const MatchItem it = sp.items[i];
+        if (it.set == ~0u) continue;
+        const int set = (int)it.set;
+        const MatchPrep p = match_prepare_warp(tb, ws, blob_xy + (size_t)set * C * MB * 2, blob_n + (size_t)set * C, lane, C, MB, RMAX, KC, GMAX,
+                                               img_flags ? img_flags + (size_t)set * C : nullptr);
+        const uint32_t w_lo = it.chunk * sp.chunk;
+        const uint32_t w_hi = p.total - w_lo < sp.chunk ? p.total : w_lo + sp.chunk;
+        match_eval_range_warp(tb, ws, lane, C, MB, KC, p.nr, w_lo, w_hi);
+        // roots of the first and the last group of the range (last r with gprefix[r] <= w)
+        int r_lo, r_hi;
+        {
+            int lo = 0, hi = p.nr;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ws.gprefix[mid] <= w_lo) lo = mid; else hi = mid; }
+            r_lo = lo;
+            lo = r_lo; hi = p.nr;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ws.gprefix[mid] <= w_hi - 1u) lo = mid; else hi = mid; }
+            r_hi = lo;
+        }
+        unsigned long long* mine = sp.partial + (size_t)i * RMAX * MATCH_PARTIAL_WORDS;
+        for (int r = r_lo + lane; r <= r_hi; r += 32) {
+            unsigned long long* q = mine + (size_t)r * MATCH_PARTIAL_WORDS;
+            q[0] = ws.best_key[r];
+            q[1] = (unsigned long long)ws.best_g[r];
+            q[2] = (unsigned long long)__double_as_longlong(ws.best_xe[4 * r + 0]);
+            q[3] = (unsigned long long)__double_as_longlong(ws.best_xe[4 * r + 1]);
+            q[4] = (unsigned long long)__double_as_longlong(ws.best_xe[4 * r + 2]);
+            q[5] = (unsigned long long)__double_as_longlong(ws.best_xe[4 * r + 3]);
+        }
+        if (lane == 0) { sp.range[2 * i] = r_lo; sp.range[2 * i + 1] = r_hi; }
+        __threadfence();                                             // every lane: its stores before the arrival below
+        __syncwarp();
+        unsigned before = 0;
+        if (lane == 0) before = atomicAdd(sp.arrive + set, 1u);
+        before = __shfl_sync(FULL_MASK, before, 0);
+        if (before != it.n_chunks - 1u) continue;
+
+        // the frame-set's last item: fold the items' results in ascending range order, emit
+        __threadfence();
+        if (lane == 0) sp.arrive[set] = 0u;
+        for (int r = lane; r < p.nr; r += 32) { ws.best_key[r] = ~0ull; ws.best_g[r] = 0u; }
+        __syncwarp();
+        for (uint32_t c = 0; c < it.n_chunks; ++c) {
+            const size_t j = (size_t)it.first + c;
+            const int a = __ldcg(sp.range + 2 * j), b = __ldcg(sp.range + 2 * j + 1);
+            const unsigned long long* theirs = sp.partial + j * RMAX * MATCH_PARTIAL_WORDS;
+            for (int r = a + lane; r <= b; r += 32) {
+                const unsigned long long* q = theirs + (size_t)r * MATCH_PARTIAL_WORDS;
+                const unsigned long long key = __ldcg(q);
+                if (key < ws.best_key[r]) {
+                    ws.best_key[r] = key;
+                    ws.best_g[r] = (uint32_t)__ldcg(q + 1);
+                    ws.best_xe[4 * r + 0] = __longlong_as_double((long long)__ldcg(q + 2));
+                    ws.best_xe[4 * r + 1] = __longlong_as_double((long long)__ldcg(q + 3));
+                    ws.best_xe[4 * r + 2] = __longlong_as_double((long long)__ldcg(q + 4));
+                    ws.best_xe[4 * r + 3] = __longlong_as_double((long long)__ldcg(q + 5));
+                }
+            }
+            __syncwarp();                                            // the next item may hand a root to another lane
+        }
+        match_emit_warp(tb, ws, set, lane, C, MB, RMAX, KC, p.nr, p.flags, obj, err_out, n_obj, set_flags, chosen, track_xy);
+        __syncwarp();
+    }
+}

@@ -1,5 +1,6 @@
 // S2 + S3 on sm_100a: epipolar correspondence search, DLT triangulation of every candidate
-// group, reprojection error, per-root argmin.  One warp per frame-set.
+// group, reprojection error, per-root argmin.  One warp per frame-set; frame-sets with more than MOCAP_MATCH_CHUNK
+// candidate groups are cut into ranges of groups that a second kernel hands to warps (match_device.cuh, MatchSplit).
 //
 // Replaces find_point_correspondance_and_object_points (reference
 // computer_code/api/helpers.py:339-421) including its inner calls of triangulate_points
@@ -13,6 +14,8 @@
 // mixed-radix number with the EARLIEST camera as least significant digit (helpers.py:394-400
 // puts the newest camera outermost).  This kernel stores only the per-camera candidate lists
 // and enumerates group indices; nothing is materialised.
+#include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "geom.cuh"
 #include "match_device.cuh"
@@ -22,7 +25,7 @@
 // register budget stays at 128)
 __global__ void __launch_bounds__(128)
 k_match_triangulate(const CameraTables* __restrict__ tb, const int32_t* blob_xy, const int32_t* blob_n,
-                    const uint32_t* __restrict__ set_list, uint32_t* set_count,
+                    const uint32_t* __restrict__ set_list, uint32_t* set_count, MatchSplit sp,
                     int n_sets, int C, int MB, int RMAX, int KC,
                     uint32_t GMAX, double* __restrict__ obj, double* __restrict__ err_out,
                     int32_t* __restrict__ n_obj, int32_t* __restrict__ set_flags, int32_t* __restrict__ chosen,
@@ -47,19 +50,21 @@ k_match_triangulate(const CameraTables* __restrict__ tb, const int32_t* blob_xy,
         }
         return;
     }
-    // persistent warps claim frame-sets from a counter: the work per frame-set varies by an order of magnitude (a few
-    // to hundreds of candidate groups), a static assignment leaves the SMs idle behind the heaviest CTAs
-    while (true) {
-        unsigned s = 0;
-        if (lane == 0) s = atomicAdd(set_count, 1u);
-        s = __shfl_sync(0xffffffffu, s, 0);
-        if (s >= (unsigned)n_sets) break;
-        const int set = (int)s;
-        match_triangulate_warp(tb, ws, blob_xy + (size_t)set * C * MB * 2, blob_n + (size_t)set * C, set, lane,
-                               C, MB, RMAX, KC, GMAX, obj, err_out, n_obj, set_flags, chosen, track_xy,
-                               img_flags ? img_flags + (size_t)set * C : nullptr);
-        __syncwarp();
-    }
+    // persistent warps claim frame-sets from sp.counters[0]; frame-sets of more than sp.chunk candidate groups become
+    // items for k_match_chunks (match_device.cuh)
+    match_sets_body(tb, ws, lane, blob_xy, blob_n, n_sets, C, MB, RMAX, KC, GMAX, sp, obj, err_out, n_obj, set_flags, chosen, track_xy, img_flags);
+}
+
+// the items k_match_triangulate left: ranges of the candidate groups of the heavy frame-sets, one warp each
+__global__ void __launch_bounds__(128)
+k_match_chunks(const CameraTables* __restrict__ tb, const int32_t* blob_xy, const int32_t* blob_n, MatchSplit sp,
+               int C, int MB, int RMAX, int KC, uint32_t GMAX, double* __restrict__ obj, double* __restrict__ err_out,
+               int32_t* __restrict__ n_obj, int32_t* __restrict__ set_flags, int32_t* __restrict__ chosen,
+               int32_t* __restrict__ track_xy, const int32_t* __restrict__ img_flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpState ws = carve_warp_state(smem_raw + warp_state_bytes(RMAX, C, KC, MB) * wid, RMAX, C, KC, MB);
+    match_chunks_body(tb, ws, lane, blob_xy, blob_n, C, MB, RMAX, KC, GMAX, sp, obj, err_out, n_obj, set_flags, chosen, track_xy, img_flags);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -111,20 +116,60 @@ k_triangulate_points(const CameraTables* __restrict__ tb, const double* __restri
     }
 }
 
+// scratch of the chunked matcher, sized for the batch: items, their partial results, arrival counters
+static int ensure_match_split(mocap_ctx* ctx, int n_sets) {
+    // room for four items per frame-set, the partial results bounded by 512 MB; frame-sets that find the list full are
+    // finished by the warp that claimed them
+    long long want = (long long)n_sets * 4 > 4096 ? (long long)n_sets * 4 : 4096;
+    const long long per_item = (long long)ctx->cfg.max_roots * MATCH_PARTIAL_WORDS * (long long)sizeof(unsigned long long);
+    if (want * per_item > (512ll << 20)) want = (512ll << 20) / per_item;
+    const int want_items = (int)want;
+    if (n_sets <= ctx->match_cap_sets && want_items <= ctx->match_item_cap) return MOCAP_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_match_items); cudaFree(ctx->d_match_partial); cudaFree(ctx->d_match_range); cudaFree(ctx->d_match_arrive);
+    ctx->d_match_items = nullptr; ctx->d_match_partial = nullptr; ctx->d_match_range = nullptr; ctx->d_match_arrive = nullptr;
+    ctx->match_cap_sets = 0; ctx->match_item_cap = 0;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_match_items, (size_t)want_items * sizeof(MatchItem)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_match_partial, (size_t)want_items * ctx->cfg.max_roots * MATCH_PARTIAL_WORDS * sizeof(unsigned long long)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_match_range, (size_t)want_items * 2 * sizeof(int)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_match_arrive, (size_t)n_sets * sizeof(unsigned)));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_match_arrive, 0, (size_t)n_sets * sizeof(unsigned), ctx->stream));   // the finishers keep it zero
+    ctx->match_cap_sets = n_sets; ctx->match_item_cap = want_items;
+    return MOCAP_OK;
+}
+
 int launch_match(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blob_n, int n_sets,
                  double* obj, double* err, int32_t* n_obj, int32_t* set_flags, int32_t* chosen) {
     if (n_sets <= 0) return MOCAP_OK;
     const mocap_config& c = ctx->cfg;
     const int warps = 4;
     const size_t smem = match_smem_bytes(c, warps);
+    const int full = ctx->num_sms * ctx->match_ctas_per_sm;
     int grid = (n_sets + warps - 1) / warps;
-    if (grid > ctx->num_sms * ctx->match_ctas_per_sm) grid = ctx->num_sms * ctx->match_ctas_per_sm;
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_match_counter, 0, sizeof(unsigned), ctx->stream));
-    k_match_triangulate<<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_tables, blob_xy, blob_n, nullptr, ctx->d_match_counter, n_sets, c.n_cam,
+    if (grid > full) grid = full;
+    MatchSplit sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.counters = ctx->d_match_counter;
+    if (ctx->match_chunk > 0) {
+        const int st = ensure_match_split(ctx, n_sets);
+        if (st) return st;
+        sp.items = static_cast<MatchItem*>(ctx->d_match_items);
+        sp.partial = ctx->d_match_partial; sp.range = ctx->d_match_range; sp.arrive = ctx->d_match_arrive;
+        sp.chunk = (uint32_t)ctx->match_chunk; sp.item_cap = (uint32_t)ctx->match_item_cap;
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_match_counter, 0, 4 * sizeof(unsigned), ctx->stream));
+    k_match_triangulate<<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_tables, blob_xy, blob_n, nullptr, nullptr, sp, n_sets, c.n_cam,
                                                                  c.max_blobs, c.max_roots, c.max_cands,
                                                                  (uint32_t)c.max_groups, obj, err, n_obj, set_flags, chosen, ctx->track_xy_cur, ctx->img_flags_cur);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 1;
+    if (sp.items) {
+        // how many items there are is known on the device only: a full persistent grid, warps without an item leave at once
+        k_match_chunks<<<full, warps * 32, smem, ctx->stream>>>(ctx->d_tables, blob_xy, blob_n, sp, c.n_cam, c.max_blobs, c.max_roots, c.max_cands,
+                                                                (uint32_t)c.max_groups, obj, err, n_obj, set_flags, chosen, ctx->track_xy_cur, ctx->img_flags_cur);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
     return MOCAP_OK;
 }
 
@@ -135,7 +180,9 @@ int launch_match_list(mocap_ctx* ctx, const int32_t* blob_xy, const int32_t* blo
     const size_t smem = match_smem_bytes(c, warps);
     int grid = (n_sets_max + warps - 1) / warps;
     if (grid > ctx->num_sms) grid = ctx->num_sms;
-    k_match_triangulate<<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_tables, blob_xy, blob_n, set_list, set_count, n_sets_max, c.n_cam,
+    MatchSplit none;
+    memset(&none, 0, sizeof(none));
+    k_match_triangulate<<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_tables, blob_xy, blob_n, set_list, set_count, none, n_sets_max, c.n_cam,
                                                                  c.max_blobs, c.max_roots, c.max_cands, (uint32_t)c.max_groups,
                                                                  obj, err, n_obj, set_flags, nullptr, ctx->track_xy_cur, ctx->d_img_flags);
     CUDA_TRY(ctx, cudaGetLastError());
@@ -161,6 +208,12 @@ int match_kernels_init(mocap_ctx* ctx) {
     int per_sm = 0;
     CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match_triangulate, 128, smem));
     ctx->match_ctas_per_sm = per_sm > 0 ? per_sm : 1;
-    CUDA_TRY(ctx, cudaMalloc(&ctx->d_match_counter, sizeof(unsigned)));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_match_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_match_counter, 4 * sizeof(unsigned)));
+    // candidate groups per item of the chunked matcher (match_device.cuh); MOCAP_MATCH_CHUNK=0: one warp per frame-set throughout
+    const char* ch = getenv("MOCAP_MATCH_CHUNK");
+    int chunk = ch && ch[0] ? atoi(ch) : MOCAP_MATCH_CHUNK;
+    if (chunk < 0) chunk = 0;
+    ctx->match_chunk = (chunk + 31) / 32 * 32;
     return MOCAP_OK;
 }

@@ -44,7 +44,8 @@ inline Tid gdim{1, 1, 1};
 inline Tid bdim{1, 1, 1};
 inline std::barrier<>* grid_barrier = nullptr;
 
-inline void warp_sync(const char* what = "warp_sync") { last_op[tid.x] = what; blk->warp[tid.x >> 5]->arrive_and_wait(); last_op[tid.x] = "running"; }
+inline unsigned slot() { return (bid.x * bdim.x + tid.x) & 4095u; }        // trace slot of this thread, unique across the CTAs of a grid
+inline void warp_sync(const char* what = "warp_sync") { last_op[slot()] = what; blk->warp[tid.x >> 5]->arrive_and_wait(); last_op[slot()] = "running"; }
 inline unsigned long long exchange(unsigned long long v, int src_lane) {      // value of lane src_lane of my warp
     blk->xchg[tid.x] = v;
     warp_sync("shuffle");
@@ -105,12 +106,12 @@ inline void simt_grid_sync() { simt::grid_barrier->arrive_and_wait(); }
 
 // ---- what the device headers call ------------------------------------------------------------------------
 #define threadIdx (simt::tid)
-inline void simt_syncthreads(const char* where) { simt::last_where[simt::tid.x] = where; simt::last_op[simt::tid.x] = "__syncthreads"; simt::blk->cta.arrive_and_wait(); simt::last_op[simt::tid.x] = "running"; }
-inline void simt_syncwarp(const char* where) { simt::last_where[simt::tid.x] = where; simt::warp_sync("__syncwarp"); }
+inline void simt_syncthreads(const char* where) { simt::last_where[simt::slot()] = where; simt::last_op[simt::slot()] = "__syncthreads"; simt::blk->cta.arrive_and_wait(); simt::last_op[simt::slot()] = "running"; }
+inline void simt_syncwarp(const char* where) { simt::last_where[simt::slot()] = where; simt::warp_sync("__syncwarp"); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 template <typename T> inline T simt_shfl(T v, int src, const char* where) {
-    simt::last_where[simt::tid.x] = where;
+    simt::last_where[simt::slot()] = where;
     static_assert(sizeof(T) <= 8, "shuffle width");
     unsigned long long raw = 0; memcpy(&raw, &v, sizeof(T));
     raw = simt::exchange(raw, src & 31);
@@ -126,7 +127,7 @@ template <typename T> inline T simt_shfl_down(T v, unsigned d, const char* where
 }
 template <typename T> inline T simt_shfl_xor(T v, int x, const char* where) { return simt_shfl(v, (int)(simt::tid.x & 31) ^ x, where); }
 inline unsigned simt_ballot(int pred, const char* where) {
-    simt::last_where[simt::tid.x] = where;
+    simt::last_where[simt::slot()] = where;
     simt::blk->xchg[simt::tid.x] = pred ? 1ull : 0ull;
     simt::warp_sync("ballot");
     unsigned r = 0;
@@ -136,7 +137,7 @@ inline unsigned simt_ballot(int pred, const char* where) {
     return r;
 }
 inline unsigned simt_match_any(unsigned v, const char* where) {
-    simt::last_where[simt::tid.x] = where;
+    simt::last_where[simt::slot()] = where;
     simt::blk->xchg[simt::tid.x] = v;
     simt::warp_sync("match_any");
     unsigned r = 0;

@@ -29,3 +29,9 @@ xy = np.ascontiguousarray(z["blob_xy"][:B].astype(np.int32)); nn = np.ascontiguo
 obj = np.zeros((B, 128, 3)); err = np.zeros((B, 128)); k = np.zeros(B, np.int32); fl = np.zeros(B, np.int32)
 ml.hc_match_triangulate(p(K), p(R), p(t), C, p(xy), p(nn), B, 64, 128, 8, ctypes.c_uint(4096), p(obj), p(err), p(k), p(fl))
 print("MATCH", k.tolist() == z["nroot"][:B].tolist())
+# the chunked matcher on a grid of 2 CTAs: items of 64 groups, partial results through "global" memory, arrival counters
+obj2 = np.zeros((B, 128, 3)); err2 = np.zeros((B, 128)); k2 = np.zeros(B, np.int32); fl2 = np.zeros(B, np.int32)
+txy = np.zeros((B, 128, C, 2), np.int32); stats = np.zeros(3, np.int64)
+ml.hc_match_triangulate_chunked(p(K), p(R), p(t), C, p(xy), p(nn), B, 64, 128, 8, ctypes.c_uint(4096), ctypes.c_uint(64), ctypes.c_uint(1024), 2,
+                                p(obj2), p(err2), p(k2), p(fl2), p(txy), p(stats))
+print("CHUNKED", bool(k2.tolist() == k.tolist() and stats[0] > 0 and stats[2] == 0 and all(np.array_equal(obj2[b, :k[b]], obj[b, :k[b]]) for b in range(B))))

@@ -158,6 +158,23 @@ def match_emu():
         assert lib.hc_match_triangulate(p(K), p(R), p(t), C, p(xy), p(n), B, MB, max_roots, max_cands, ctypes.c_uint(max_groups),
                                         p(obj), p(err), p(k), p(fl)) == 0
         return {"obj": obj, "err": err, "n": k, "flags": fl}
+
+    def chunked(K, R, t, blob_xy, blob_n, chunk, item_cap, n_ctas=3, max_roots=128, max_cands=8, max_groups=4096):
+        """k_match_triangulate + k_match_chunks on an emulated grid: frame-sets of more than ``chunk`` groups go to several warps"""
+        C = len(R)
+        B = blob_n.shape[0]
+        MB = blob_xy.shape[2]
+        K = np.ascontiguousarray(np.stack([K] * C) if np.ndim(K) == 2 else K, dtype=np.float64)
+        R = np.ascontiguousarray(R, dtype=np.float64); t = np.ascontiguousarray(np.reshape(t, (C, 3)), dtype=np.float64)
+        xy = np.ascontiguousarray(blob_xy, dtype=np.int32); n = np.ascontiguousarray(blob_n, dtype=np.int32)
+        obj = np.zeros((B, max_roots, 3)); err = np.zeros((B, max_roots))
+        k = np.zeros(B, np.int32); fl = np.zeros(B, np.int32); txy = np.zeros((B, max_roots, C, 2), np.int32); stats = np.zeros(3, np.int64)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        assert lib.hc_match_triangulate_chunked(p(K), p(R), p(t), C, p(xy), p(n), B, MB, max_roots, max_cands, ctypes.c_uint(max_groups),
+                                                ctypes.c_uint(chunk), ctypes.c_uint(item_cap), n_ctas,
+                                                p(obj), p(err), p(k), p(fl), p(txy), p(stats)) == 0
+        return {"obj": obj, "err": err, "n": k, "flags": fl, "track_xy": txy, "items": int(stats[0]), "claimed": int(stats[1]), "armed": int(stats[2])}
+    match.chunked = chunked
     return match
 
 
@@ -174,6 +191,47 @@ def test_matcher_device_code_vs_reference_golden(match_emu, name):
         if k[b]:
             assert np.abs(d["obj"][b, :k[b]] - z["obj"][b, :k[b]]).max() <= X_TOL
             assert np.allclose(d["err"][b, :k[b]], z["err"][b, :k[b]], rtol=ERR_RTOL, atol=1e-12)
+
+
+def test_chunked_matcher_equals_one_warp_per_frame_set(match_emu):
+    """Frame-sets cut into items of `chunk` candidate groups and folded back together (k_match_chunks) give bit for bit what
+    one warp walking the whole frame-set gives -- points, errors, counts, flags, the winners' pixels -- for chunks of one
+    round (32 groups, every root spans several items), for larger chunks (frame-sets on both sides of the threshold), with
+    an item list that is too short (the frame-sets that do not fit are finished by the claiming warp), and with ties
+    between groups in different items (duplicated blobs: np.argmin keeps the first group)."""
+    z = load_golden("pipe_c8_m16", frames=False)
+    B = 10
+    xy, nb = z["blob_xy"][:B].copy(), z["blob_n"][:B].copy()
+    # ties across items: frame-set 1 sees the same blob twice in cameras 2 and 5
+    for c in (2, 5):
+        k = int(nb[1, c])
+        xy[1, c, k] = xy[1, c, 0]; nb[1, c] = k + 1
+    one = match_emu.chunked(z["K"], z["R"], z["t"], xy, nb, chunk=0, item_cap=0)
+    ref = match_emu(z["K"], z["R"], z["t"], xy, nb)
+    assert one["items"] == 0 and np.array_equal(one["n"], ref["n"]) and np.array_equal(one["flags"], ref["flags"])
+
+    def same(a, b):
+        if not (np.array_equal(a["n"], b["n"]) and np.array_equal(a["flags"], b["flags"])):
+            return False
+        for s in range(B):
+            k = a["n"][s]
+            if not (np.array_equal(a["obj"][s, :k], b["obj"][s, :k]) and np.array_equal(a["err"][s, :k], b["err"][s, :k])
+                    and np.array_equal(a["track_xy"][s, :k], b["track_xy"][s, :k])):
+                return False
+        return True
+    for s in range(B):
+        k = ref["n"][s]
+        assert np.array_equal(one["obj"][s, :k], ref["obj"][s, :k]) and np.array_equal(one["err"][s, :k], ref["err"][s, :k])
+    many = match_emu.chunked(z["K"], z["R"], z["t"], xy, nb, chunk=32, item_cap=4096)
+    assert many["items"] > 5 * B and many["claimed"] >= many["items"] and many["armed"] == 0 and same(many, one)
+    some = match_emu.chunked(z["K"], z["R"], z["t"], xy, nb, chunk=256, item_cap=4096, n_ctas=2)
+    assert 0 < some["items"] < many["items"] and some["armed"] == 0 and same(some, one)
+    short = match_emu.chunked(z["K"], z["R"], z["t"], xy, nb, chunk=32, item_cap=many["items"] // 3)
+    assert short["items"] == many["items"] and short["armed"] == 0 and same(short, one)
+    # the capacity flags travel with the frame-set through the items
+    tight = match_emu.chunked(z["K"], z["R"], z["t"], xy, nb, chunk=32, item_cap=4096, max_roots=8, max_groups=40)
+    tight1 = match_emu.chunked(z["K"], z["R"], z["t"], xy, nb, chunk=0, item_cap=0, max_roots=8, max_groups=40)
+    assert tight1["flags"].any() and same(tight, tight1)
 
 
 @pytest.mark.parametrize("name", ["pipe_c2_m1", "pipe_c4_m4"])
@@ -335,7 +393,7 @@ def test_device_code_has_no_unintended_data_races(tmp_path):
     r = subprocess.run([shutil.which("python") or "python", os.path.join(HC, "tsan_blob_match_run.py"), ROOT, libs["blob"], libs["match"]],
                        capture_output=True, text=True, env=env, timeout=280)
     out = r.stdout + r.stderr
-    assert out.count("BLOB") == 4 and "MATCH True" in out, out[-2000:]
+    assert out.count("BLOB") == 4 and "MATCH True" in out and "CHUNKED True" in out, out[-2000:]
     assert "WARNING: ThreadSanitizer" not in out, out[:4000]
 
 
