@@ -1239,7 +1239,8 @@ def test_detect_reproduces_retr_tree_on_blobs_with_holes(torch):
             out = c2.pipeline(torch.from_numpy(frames).cuda())
             assert np.array_equal(out["flags"].cpu().numpy(), flags), mode
         d2 = c2.detect(torch.from_numpy(frames).cuda())
-        assert torch.equal(d2["n"], d["n"]) and torch.equal(d2["xy"], d["xy"])
+        live = torch.arange(d["xy"].shape[1], device="cuda")[None, :] < d["n"][:, None]      # rows past the count are unspecified
+        assert torch.equal(d2["n"], d["n"]) and torch.equal(d2["xy"][live], d["xy"][live])
     s = pkg.MocapSession([np.eye(3)])
     for f in (int(np.argmax(z["has_hole"].astype(bool) & fits)), int(np.argmax(~z["has_hole"].astype(bool) & fits))):
         _, pts = pkg.find_dot(as3(frames[f, 0]), session=s)
