@@ -416,7 +416,26 @@ def run_gpu_arm(args):
         ba_R = [R0.clone() for _ in range(n_bufs * n_sub)]
         ba_t = [t0_.clone() for _ in range(n_bufs * n_sub)]
         ba_rep = [None] * (n_bufs * n_sub)
-        side = torch.cuda.Stream(device=dev)
+        # the n_sub solves of a step are independent.  k_ba_solve is one cooperative grid whose serial sections (dense
+        # solves, tridiagonalisation) leave most of it waiting at barriers: several solves side by side, each on a share of
+        # the SMs (own context = own workspace, own stream), overlap one solve's serial sections with another's tiles
+        # (tools/ba_grid_probe.py: 4 solves of 18 800 points take 5.24 ms one after the other on 148 CTAs, 3.87 ms as
+        # 2 x 74 CTAs, 5.18 ms for SIX as 3 x 49)
+        ba_k = max(1, min(int(args.ba_streams), n_sub))
+        if ba_k > 1:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            saved = os.environ.get("MOCAP_BA_GRID")
+            os.environ["MOCAP_BA_GRID"] = str(max(1, sms // ba_k))
+            try:
+                ba_ctx = [pkg.MocapContext(N_CAM, WIDTH, HEIGHT, device=local, max_roots=MAX_ROOTS) for _ in range(ba_k)]
+            finally:
+                if saved is None: os.environ.pop("MOCAP_BA_GRID", None)
+                else: os.environ["MOCAP_BA_GRID"] = saved
+            for c_ in ba_ctx:
+                c_.set_cameras([K] * N_CAM, poses)
+        else:
+            ba_ctx = [ctx]
+        sides = [torch.cuda.Stream(device=dev) for _ in range(ba_k)]
         tracks_ready = [torch.cuda.Event() for _ in range(n_bufs)]
         ba_done = [None] * n_bufs
         ba_ms_events = []
@@ -425,24 +444,27 @@ def run_gpu_arm(args):
         """tracks of buffer k -> n_sub bundle adjustments, enqueued on the side stream"""
         main = torch.cuda.current_stream(dev)
         tracks_ready[k].record(main)
-        with torch.cuda.stream(side):
-            side.wait_event(tracks_ready[k])
-            for j in range(n_sub):
-                i = k * n_sub + j
-                sl = slice(j * BA_BATCH, (j + 1) * BA_BATCH)
-                tr = {key: outs[k][key][sl] for key in ("track_xy", "n", "err")}
-                ctx.tracks_to_observations_dev(tr, max_err=BA_MAX_ERR, capacity=cap, out=ba_obs[i])
-                ba_R[i].copy_(R0); ba_t[i].copy_(t0_)
-                if timed:
-                    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    ea.record(side)
-                ba_rep[i] = ctx.bundle_adjust_dev(ba_obs[i]["obs"], ba_obs[i]["mask"], ba_R[i], ba_t[i], n_points=ba_obs[i]["n"], report=ba_rep[i])
-                if timed:
-                    eb.record(side)
-                    ba_ms_events.append((ea, eb))
-            ev = torch.cuda.Event()
-            ev.record(side)
-            ba_done[k] = ev
+        done = []
+        for q, side in enumerate(sides):
+            with torch.cuda.stream(side):
+                side.wait_event(tracks_ready[k])
+                for j in range(q, n_sub, len(sides)):
+                    i = k * n_sub + j
+                    sl = slice(j * BA_BATCH, (j + 1) * BA_BATCH)
+                    tr = {key: outs[k][key][sl] for key in ("track_xy", "n", "err")}
+                    ba_ctx[q].tracks_to_observations_dev(tr, max_err=BA_MAX_ERR, capacity=cap, out=ba_obs[i])
+                    ba_R[i].copy_(R0); ba_t[i].copy_(t0_)
+                    if timed:
+                        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        ea.record(side)
+                    ba_rep[i] = ba_ctx[q].bundle_adjust_dev(ba_obs[i]["obs"], ba_obs[i]["mask"], ba_R[i], ba_t[i], n_points=ba_obs[i]["n"], report=ba_rep[i])
+                    if timed:
+                        eb.record(side)
+                        ba_ms_events.append((ea, eb))
+                ev = torch.cuda.Event()
+                ev.record(side)
+                done.append(ev)
+        ba_done[k] = done
 
     def step(timed=False):
         k = step_no[0] % n_bufs
@@ -451,7 +473,8 @@ def run_gpu_arm(args):
             pending[k].wait()                # this buffer's previous all-gather has read it
             pending[k] = None
         if with_ba and ba_done[k] is not None:
-            torch.cuda.current_stream(dev).wait_event(ba_done[k])    # the S4 that read this buffer has finished
+            for ev in ba_done[k]:
+                torch.cuda.current_stream(dev).wait_event(ev)        # the S4 that read this buffer has finished
         ctx.pipeline(batch, out=outs[k])
         if with_ba:
             run_s4(k, timed)
@@ -465,8 +488,8 @@ def run_gpu_arm(args):
                 w.wait()
                 pending[k] = None
         if with_ba:
-            for ev in ba_done:
-                if ev is not None:
+            for evs in ba_done:
+                for ev in evs or []:
                     torch.cuda.current_stream(dev).wait_event(ev)
 
     def sync_all():
@@ -487,7 +510,9 @@ def run_gpu_arm(args):
     # ---- timed region: resident inputs -----------------------------------------------------
     ctx.enable_kernel_timing(True)
     ctx.detect_kernel_ms(reset=True)
-    launches0 = ctx.launch_count()
+    def all_launches():
+        return ctx.launch_count() + (sum(c_.launch_count() for c_ in ba_ctx if c_ is not ctx) if with_ba else 0)
+    launches0 = all_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
@@ -500,7 +525,7 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    launches = ctx.launch_count() - launches0
+    launches = all_launches() - launches0
     if world > 1:
         launches += args.steps              # the NCCL all-gather kernel
     kern_ms, kern_n = ctx.detect_kernel_ms(reset=True)
@@ -543,7 +568,8 @@ def run_gpu_arm(args):
               "prefit_iterations": float(np.mean([r["prefit_iterations"] for r in reps])), "n_fev": float(np.mean([r["n_fev"] for r in reps])),
               "phase_ms": [float(v) for v in np.mean([r["phase_ms"] for r in reps], axis=0)],
               "pose_error_vs_true_rig": {"rotation_max_abs": rot_err, "translation_max_abs_after_scale": t_err},
-              "overlap": "side stream; the solves of step k run while step k+1 streams"}
+              "overlap": "side stream; the solves of step k run while step k+1 streams",
+              "side_streams": ba_k, "ctas_per_solve": int(os.environ.get("MOCAP_BA_GRID", 0)) or (torch.cuda.get_device_properties(dev).multi_processor_count // ba_k)}
         if any(r["status"] not in (1, 2, 3, 4) for r in reps) or rot_err > 2e-2 or t_err > 5e-2:
             problems.append(f"rank {rank}: S4 did not converge to the true rig: {s4}")
     if world > 1:
@@ -685,6 +711,8 @@ def main():
                     help="c4m4 (default): BASELINE config 2, the configuration the metric is quoted on; c8m16: 8 cameras, 16 markers, 4000 "
                          "frame-sets per GPU per step -- at N = 1 BASELINE config 3 (S1-S3 plus one S4 per 1000 frame-sets), at N > 1 "
                          "config 4 (S1-S3, round-robin shards, one NCCL all-gather of tracks per batch)")
+    ap.add_argument("--ba-streams", type=int, default=1,
+                    help="c8m16 with S4: the solves of a step side by side on this many contexts / streams, each on a share of the SMs")
     ap.add_argument("--no-ba", action="store_true", help="c8m16 at N = 1 without S4 (the S1-S3 figure of the config-3 shape)")
     ap.add_argument("--profile", action="store_true",
                     help="resident steps only (no e2e, no CPU baseline): for runs under ncu; prints no bench line")
