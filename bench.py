@@ -424,15 +424,10 @@ def run_gpu_arm(args):
         ba_k = max(1, min(int(args.ba_streams), n_sub))
         if ba_k > 1:
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            saved = os.environ.get("MOCAP_BA_GRID")
-            os.environ["MOCAP_BA_GRID"] = str(max(1, sms // ba_k))
-            try:
-                ba_ctx = [pkg.MocapContext(N_CAM, WIDTH, HEIGHT, device=local, max_roots=MAX_ROOTS) for _ in range(ba_k)]
-            finally:
-                if saved is None: os.environ.pop("MOCAP_BA_GRID", None)
-                else: os.environ["MOCAP_BA_GRID"] = saved
+            ba_ctx = [pkg.MocapContext(N_CAM, WIDTH, HEIGHT, device=local, max_roots=MAX_ROOTS) for _ in range(ba_k)]
             for c_ in ba_ctx:
                 c_.set_cameras([K] * N_CAM, poses)
+                c_.set_ba_grid(max(1, sms // ba_k))
         else:
             ba_ctx = [ctx]
         sides = [torch.cuda.Stream(device=dev) for _ in range(ba_k)]
@@ -569,7 +564,7 @@ def run_gpu_arm(args):
               "phase_ms": [float(v) for v in np.mean([r["phase_ms"] for r in reps], axis=0)],
               "pose_error_vs_true_rig": {"rotation_max_abs": rot_err, "translation_max_abs_after_scale": t_err},
               "overlap": "side stream; the solves of step k run while step k+1 streams",
-              "side_streams": ba_k, "ctas_per_solve": int(os.environ.get("MOCAP_BA_GRID", 0)) or (torch.cuda.get_device_properties(dev).multi_processor_count // ba_k)}
+              "side_streams": ba_k, "ctas_per_solve": torch.cuda.get_device_properties(dev).multi_processor_count // ba_k}
         if any(r["status"] not in (1, 2, 3, 4) for r in reps) or rot_err > 2e-2 or t_err > 5e-2:
             problems.append(f"rank {rank}: S4 did not converge to the true rig: {s4}")
     if world > 1:
@@ -711,7 +706,7 @@ def main():
                     help="c4m4 (default): BASELINE config 2, the configuration the metric is quoted on; c8m16: 8 cameras, 16 markers, 4000 "
                          "frame-sets per GPU per step -- at N = 1 BASELINE config 3 (S1-S3 plus one S4 per 1000 frame-sets), at N > 1 "
                          "config 4 (S1-S3, round-robin shards, one NCCL all-gather of tracks per batch)")
-    ap.add_argument("--ba-streams", type=int, default=1,
+    ap.add_argument("--ba-streams", type=int, default=4,
                     help="c8m16 with S4: the solves of a step side by side on this many contexts / streams, each on a share of the SMs")
     ap.add_argument("--no-ba", action="store_true", help="c8m16 at N = 1 without S4 (the S1-S3 figure of the config-3 shape)")
     ap.add_argument("--profile", action="store_true",

@@ -273,6 +273,13 @@ MOCAP_API int  mocap_bundle_adjust_host(mocap_ctx* ctx, const double* obs, const
 MOCAP_API int  mocap_bundle_adjust_dev(mocap_ctx* ctx, const double* obs, const uint8_t* mask, int n_points_max,
                              const int32_t* n_points, double* R, double* t, const mocap_ba_options* opt,
                              mocap_ba_report* report);
+/* CTAs of k_ba_solve for this context (1 .. number of SMs; 0 = the default, one per SM).  One solve is a cooperative
+ * grid whose serial sections (dense solves, tridiagonalisation) leave most CTAs waiting at the grid barrier, so
+ * INDEPENDENT solves -- the reference runs one bundle_adjustment per recorded batch (index.py:249-276), a session with
+ * several batches has several -- finish sooner side by side: K contexts on K streams with SMs / K CTAs each
+ * (measured, 8 cameras x 18 800 points: 4 solves 5.24 ms in turn on 148 CTAs, 3.87 ms as 2 x 74, 3.2 ms as 4 x 37).
+ * The result does not depend on the number of CTAs. */
+MOCAP_API int  mocap_set_ba_grid(mocap_ctx* ctx, int n_ctas);
 /* Matcher output of a batch -> the explicit correspondences S4 consumes (BASELINE config 3: S1-S3, then one
  * bundle adjustment per batch), on the device: track_xy int32 [n_frame_sets][max_roots][n_cam][2] as written by
  * mocap_pipeline_tracks_dev ((-1, -1) = no view), n_obj / err the matcher's outputs; tracks whose reprojection

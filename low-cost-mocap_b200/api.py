@@ -272,6 +272,11 @@ class MocapContext:
                                                               float(max_err), _ptr(out["obs"]), _ptr(out["mask"]), _ptr(out["n"]), cap))
         return out
 
+    def set_ba_grid(self, n_ctas=0):
+        """CTAs of the device-resident bundle adjustment of this context (0: one per SM).  Independent solves finish sooner
+        side by side: K contexts on K streams with SMs // K CTAs each (mocap_set_ba_grid, include/mocap_b200.h)."""
+        self._check(self.lib.mocap_set_ba_grid(self.h, int(n_ctas)))
+
     def bundle_adjust_dev(self, obs, mask, R, t, n_points=None, report=None, ftol=1e-2, max_nfev=0, prefit=True, jacobian=1,
                           prefit_max_iter=50):
         """S4 wholly on the device (mocap_bundle_adjust_dev): obs f64 [P, C, 2], mask uint8 [P, C], R f64 [C, 3, 3] and

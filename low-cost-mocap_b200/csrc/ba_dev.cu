@@ -132,6 +132,16 @@ static int ba_workspace(mocap_ctx* ctx, int m_max, int n_sets, BAWorkspace& W, i
 
 extern "C" {
 
+int mocap_set_ba_grid(mocap_ctx* ctx, int n_ctas) {
+    if (!ctx) return MOCAP_EINVAL;
+    if (ctx->ba_grid < 1) return mocap_fail(ctx, MOCAP_EINVAL, "bundle adjustment is not available for this context (cameras: %d)", ctx->cfg.n_cam);
+    if (n_ctas < 0 || n_ctas > ctx->num_sms)
+        return mocap_fail(ctx, MOCAP_EINVAL, "mocap_set_ba_grid: %d CTAs asked, 1 .. %d possible (0: default)", n_ctas, ctx->num_sms);
+    // the workspace is carved per call from the grid in force (ba_workspace), the barrier words keep their place
+    ctx->ba_grid = n_ctas == 0 ? ctx->num_sms : n_ctas;
+    return MOCAP_OK;
+}
+
 int mocap_tracks_to_observations_dev(mocap_ctx* ctx, const int32_t* track_xy, const int32_t* n_obj, const double* err,
                                      int n_frame_sets, double max_err, double* obs, uint8_t* mask, int32_t* n_points,
                                      int capacity) {

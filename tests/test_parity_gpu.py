@@ -1145,6 +1145,42 @@ def test_ba_device_engine_is_reproducible(torch):
         assert np.array_equal(p["R"], q["R"]) and np.array_equal(p["t"], q["t"])
 
 
+def test_ba_grid_setter_and_solves_side_by_side(torch):
+    """mocap_set_ba_grid: the result of a solve does not depend on the number of CTAs, two contexts with half of the SMs
+    each run their solves on two streams side by side with the same result, and values outside 0 .. SMs are refused."""
+    obs, mask, _, start, K, _ = _tracks_case(8, 3000, seed=5)
+    ctx = _ctx(8)
+    ctx.set_cameras([K] * 8, start)
+    ref, rep = ctx.bundle_adjust(obs, mask, start)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for n in (1, 37, sms // 2, 0):
+        ctx.set_ba_grid(n)
+        out, r = ctx.bundle_adjust(obs, mask, start)
+        assert r["status"] == rep["status"] and r["n_fev"] == rep["n_fev"] and abs(r["cost_final"] - rep["cost_final"]) <= 1e-9 * rep["cost_final"]
+        for a, b in zip(out, ref):
+            assert np.abs(a["R"] - b["R"]).max() < 1e-10 and np.abs(a["t"] - b["t"]).max() < 1e-10
+    for bad in (-1, sms + 1):
+        with pytest.raises(pkg.MocapError):
+            ctx.set_ba_grid(bad)
+    d_obs, d_mask = torch.from_numpy(obs).cuda(), torch.from_numpy(mask).cuda()
+    R0 = torch.from_numpy(np.stack([np.asarray(p["R"]) for p in start])).cuda().contiguous()
+    t0 = torch.from_numpy(np.stack([np.asarray(p["t"]).reshape(3) for p in start])).cuda().contiguous()
+    pair = [_ctx(8), _ctx(8)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    Rs, ts = [R0.clone() for _ in range(4)], [t0.clone() for _ in range(4)]
+    for c in pair:
+        c.set_cameras([K] * 8, start)
+        c.set_ba_grid(sms // 2)
+    torch.cuda.synchronize()
+    for i in range(4):
+        with torch.cuda.stream(streams[i % 2]):
+            pair[i % 2].bundle_adjust_dev(d_obs, d_mask, Rs[i], ts[i])
+    torch.cuda.synchronize()
+    for i in range(4):
+        assert torch.equal(Rs[i], Rs[0]) and torch.equal(ts[i], ts[0])
+        assert np.abs(Rs[i].cpu().numpy() - np.stack([p["R"] for p in ref])).max() < 1e-10
+
+
 def test_pipeline_tracks_equal_chosen_correspondences(torch):
     """mocap_pipeline_tracks_dev leaves the pixel of the winning correspondence per camera; it must be the blob the
     `chosen` indices of the separate matcher name, and the device compaction must equal the torch one."""
